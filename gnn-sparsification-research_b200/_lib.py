@@ -1,0 +1,108 @@
+"""ctypes binding of libgsp.so — the only way the Python layer reaches the CUDA kernels.
+
+The prototypes mirror include/gsp.h one to one. There is no CPU fallback: if the library is missing or
+no CUDA device is present, every compute entry point raises (loudly) instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libgsp.so")
+
+SELECT_BINS = 2048
+SELECT_PASSES = 6
+SELECT_STATE_BYTES = 16384
+
+
+class GspError(RuntimeError):
+    pass
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [
+        ("num_nodes", C.c_int64), ("num_input_edges", C.c_int64), ("nnz", C.c_int64),
+        ("num_undirected", C.c_int64), ("max_degree", C.c_int64), ("sum_degree_sq", C.c_double),
+        ("symmetric", C.c_int32), ("input_canonical", C.c_int32), ("unit_weights", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_INT = C.c_int
+_F64 = C.c_double
+
+# name -> (restype, argtypes); every symbol include/gsp.h declares
+PROTOTYPES = {
+    "gsp_version": (_INT, []),
+    "gsp_last_error": (C.c_char_p, []),
+    "gsp_graph_create": (_INT, [_I64, _I64, _P, _P, _P, _P, C.POINTER(_P)]),
+    "gsp_graph_destroy": (None, [_P]),
+    "gsp_graph_get_info": (_INT, [_P, C.POINTER(GraphInfo)]),
+    "gsp_graph_export": (_INT, [_P, _P, _P, _P, _P, _P]),
+    "gsp_graph_degrees": (_INT, [_P, _P, _P]),
+    "gsp_graph_undirected_ids": (_INT, [_P, _P, _P]),
+    "gsp_jaccard": (_INT, [_P, _I64, _I64, _P, _P, _P]),
+    "gsp_adamic_adar": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "gsp_aa_node_weights": (_INT, [_P, _P, _P]),
+    "gsp_degree_product": (_INT, [_P, _I64, _I64, _P, _P]),
+    "gsp_featcos_normalize_f32": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
+    "gsp_featcos_f32": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),
+    "gsp_featcos_normalize_f64": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
+    "gsp_featcos_f64": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),
+    "gsp_approx_er_partial": (_INT, [_P, _P, _I64, _I32, _I32, _F64, _F64, _I64, _I64, _P, _P, _P]),
+    "gsp_er_finalize": (_INT, [_P, _I64, _P]),
+    "gsp_select_begin": (_INT, [_P, _I64, _INT, _P]),
+    "gsp_select_histogram": (_INT, [_P, _I64, _P, _P, _INT, _P, _P]),
+    "gsp_select_pick": (_INT, [_P, _P, _INT, _P]),
+    "gsp_select_count_ties": (_INT, [_P, _I64, _P, _P, _P, _P]),
+    "gsp_select_write_mask": (_INT, [_P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
+    "gsp_select_mask": (_INT, [_P, _I64, _I64, _INT, _P, _INT, _P, _P]),
+    "gsp_degree_aware_guarantee": (_INT, [_P, _P, _I64, _I64, _I32, _P, _P, _P]),
+    "gsp_compact_edges": (_INT, [_P, _I64, _I64, _P, _P, _INT, _P, _I64, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libgsp.so (no device needed for loading; compute calls need CUDA)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GspError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the sparsification engine."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise GspError("the sparsification engine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().gsp_last_error()
+        raise GspError(f"libgsp error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

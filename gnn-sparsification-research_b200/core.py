@@ -1,0 +1,311 @@
+"""`GraphSparsifier` — drop-in for reference `src/sparsification/core.py:24-490`, executed on a B200.
+
+Same constructor, attributes, method names, argument order, return types and error behaviour as the
+reference class; every score vector and keep-mask is produced by the CUDA kernels of libgsp.so (through
+`engine.py`). Scores are cached on the device; the NumPy arrays the reference API promises are
+materialised lazily (`compute_scores` returns `np.ndarray[float64]` in canonical CSR order, exactly
+like the reference). There is no CPU fallback: without CUDA every scoring/selection call raises.
+
+Reference behaviours reproduced on purpose:
+  * positional aliasing — scores are in canonical-CSR order but masks index `edge_index` columns by
+    position (`core.py:239-242`), also for unsorted or duplicated `edge_index`;
+  * `num_keep = int(num_edges * r)` and Python's slicing quirks (`order[-0:]` is everything);
+  * ties resolved as a stable argsort would (top-k keeps the highest positions of the boundary tie
+    class, bottom-k the lowest) — the reference's default argsort is an unstable SIMD sort, so this is
+    the reproducible form of its contract;
+  * `random` scores come from NumPy's global legacy RNG, `sparsify_sampled` draws with NumPy's PCG64
+    `Generator.choice` on the host (its sequential fp64 cumsum cannot be matched bit-for-bit by a
+    parallel scan) — RNG streams are part of the reference's observable behaviour.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import DeviceGraph, compact_edges, degree_aware_guarantee, select_mask
+
+
+class GraphSparsifier:
+    """Engine for graph sparsification via edge metric thresholding (reference core.py:24)."""
+
+    SUPPORTED_METRICS = {
+        "jaccard", "adamic-adar", "adamic_adar", "aa", "effective_resistance", "effective-resistance", "er",
+        "approx_effective_resistance", "approx_er", "random", "rand", "degree", "feature_cosine", "feature-cosine",
+    }
+    _DISTANCE_METRICS = {"effective_resistance", "approx_effective_resistance"}
+
+    def __init__(self, data, device: str, compute_device: Optional[str] = None) -> None:
+        self.data = data
+        self.device = device
+        self.num_nodes = data.num_nodes
+        self.num_edges = data.edge_index.size(1)
+        self.verbose: bool = False
+        self._score_cache: Dict[str, np.ndarray] = {}
+        # --- B200 engine state (built lazily so argument validation needs no device) ---
+        self._compute_device = compute_device
+        self._graph: Optional[DeviceGraph] = None
+        self._ei_dev: Optional[torch.Tensor] = None
+        self._dev_scores: Dict[str, torch.Tensor] = {}
+        self._xhat: Optional[torch.Tensor] = None
+        # extensions (not in the reference signature): ApproxER knobs, AA weight source
+        self.approx_er_options = dict(epsilon=0.3, seed=42, max_cg_iters=500, cg_tol=1e-6, k=None, projection=None)
+        self.aa_weights = "numpy"   # "numpy": libm-defined constant table from NumPy (bit parity); "device": CUDA log
+
+    # ------------------------------------------------------------------------------ engine plumbing
+    @property
+    def scores(self) -> Dict[str, np.ndarray]:
+        """Alias some reference callers read (scripts/nb07_synthetic/run_synthetic_hpo.py:275)."""
+        return self._score_cache
+
+    def _cuda_device(self) -> torch.device:
+        _lib.require_cuda()
+        if self._compute_device is not None:
+            return torch.device(self._compute_device)
+        ei = self.data.edge_index
+        if ei.is_cuda:
+            return ei.device
+        dev = torch.device(self.device) if isinstance(self.device, str) else self.device
+        if isinstance(dev, torch.device) and dev.type == "cuda":
+            return torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
+        return torch.device("cuda", torch.cuda.current_device())
+
+    @property
+    def graph(self) -> DeviceGraph:
+        if self._graph is None:
+            dev = self._cuda_device()
+            ei = self.data.edge_index
+            if ei.dtype != torch.int64:
+                ei = ei.long()
+            self._ei_dev = ei.to(dev, non_blocking=True).contiguous()
+            self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
+        return self._graph
+
+    @property
+    def adj(self):
+        """SciPy CSR view of the canonical adjacency (reference attribute `adj`, core.py:71-74); host copy."""
+        import scipy.sparse as sp
+
+        g = self.graph
+        indptr, indices, data, _ = g.export(with_data=True)
+        return sp.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
+                             shape=(self.num_nodes, self.num_nodes))
+
+    # ------------------------------------------------------------------------------ name handling
+    def _normalize_metric_name(self, metric: str) -> str:
+        """reference core.py:118-138."""
+        key = metric.lower().replace("-", "_").replace(" ", "_")
+        table = {
+            "jaccard": "jaccard", "adamic_adar": "adamic_adar", "aa": "adamic_adar",
+            "effective_resistance": "effective_resistance", "er": "effective_resistance",
+            "approx_effective_resistance": "approx_effective_resistance", "approx_er": "approx_effective_resistance",
+            "random": "random", "rand": "random", "degree": "degree", "feature_cosine": "feature_cosine",
+        }
+        if key in table:
+            return table[key]
+        raise ValueError(f"Metric '{metric}' not supported. " f"Choose from: {self.SUPPORTED_METRICS}")
+
+    def _scores_to_cost(self, scores: np.ndarray, metric: str) -> np.ndarray:
+        """Similarity -> distance for the metric backbone, d = 1/p - 1 (reference core.py:82-116)."""
+        key = GraphSparsifier._normalize_metric_name(self, metric)
+        if key in GraphSparsifier._DISTANCE_METRICS:
+            similarity = 1.0 / np.maximum(scores, 1e-10)
+        else:
+            similarity = scores.copy()
+        top = similarity.max()
+        if top <= 0:
+            return np.ones_like(scores)
+        proximity = similarity / top
+        positive = proximity[proximity > 0]
+        floor = (positive.min() * 0.01) if len(positive) > 0 else 1e-6
+        proximity[proximity <= 0] = floor
+        return 1.0 / proximity - 1.0
+
+    # ------------------------------------------------------------------------------ scoring
+    def _device_scores(self, metric: str) -> torch.Tensor:
+        """fp64 score tensor on the GPU, canonical CSR order, length nnz (cached per metric)."""
+        key = self._normalize_metric_name(metric)
+        if key in self._dev_scores:
+            return self._dev_scores[key]
+        g = self.graph
+        if key in self._score_cache:                       # injected / host-side scores: upload once
+            t = torch.from_numpy(np.ascontiguousarray(self._score_cache[key], dtype=np.float64)).to(g.device)
+        elif key == "jaccard":
+            t = g.jaccard()
+        elif key == "adamic_adar":
+            t = g.adamic_adar(self._aa_node_weights())
+        elif key == "effective_resistance":
+            t = self._exact_effective_resistance()
+        elif key == "approx_effective_resistance":
+            t = self._approx_effective_resistance()
+        elif key == "random":
+            # reference core.py:165-166: NumPy's global legacy RNG (host state is the behaviour)
+            t = torch.from_numpy(np.random.rand(g.nnz)).to(g.device)
+        elif key == "degree":
+            t = g.degree_product()
+        elif key == "feature_cosine":
+            if getattr(self.data, "x", None) is None:
+                raise ValueError("feature_cosine requires node features (data.x)")
+            if self._xhat is None:
+                self._xhat = g.normalize_features(self.data.x)
+            t = g.feature_cosine(self._xhat)
+        else:  # unreachable
+            raise ValueError(f"Internal error: Unhandled metric '{key}'")
+        self._dev_scores[key] = t
+        return t
+
+    def _aa_node_weights(self) -> Optional[torch.Tensor]:
+        """Adamic-Adar node weights 1/sqrt(max(log(deg+1),1e-10)) (reference metrics.py:104-108).
+
+        The weight depends only on the integer degree, and its last bit is defined by NumPy's libm/SIMD
+        `log`. "numpy" evaluates the reference expression once per distinct degree value (a constant table
+        of at most max_degree+1 entries) and gathers it on the device, so scores are bit-equal to the
+        reference; "device" uses CUDA's log (<= 1 ulp apart, scores within 1e-6)."""
+        if self.aa_weights != "numpy":
+            return None
+        g = self.graph
+        table = np.arange(g.max_degree + 1, dtype=np.float64)
+        table = 1.0 / np.sqrt(np.maximum(np.log(table + 1), 1e-10))
+        table_dev = torch.from_numpy(table).to(g.device)
+        return table_dev[g.degrees().long()]
+
+    def _approx_effective_resistance(self) -> torch.Tensor:
+        from .metrics import _approx_er_on_graph
+        return _approx_er_on_graph(self.graph, **self.approx_er_options)
+
+    def _exact_effective_resistance(self) -> torch.Tensor:
+        from .metrics import _exact_er_on_graph
+        return _exact_er_on_graph(self.graph)
+
+    def compute_scores(self, metric: str) -> np.ndarray:
+        """Edge scores as float64 ndarray in canonical CSR order (reference core.py:140-191)."""
+        key = self._normalize_metric_name(metric)
+        if key not in self._score_cache:
+            self._score_cache[key] = self._device_scores(key).cpu().numpy()
+        return self._score_cache[key]
+
+    # ------------------------------------------------------------------------------ selection
+    @staticmethod
+    def _check_ratio(retention_ratio: float) -> None:
+        if not 0 < retention_ratio <= 1:
+            raise ValueError(f"retention_ratio must be in (0, 1], got {retention_ratio}")
+
+    def _full(self, return_mask: bool):
+        if return_mask:
+            return self.data.clone(), torch.ones(self.num_edges, dtype=torch.bool)
+        return self.data.clone()
+
+    def _finish(self, mask_dev: torch.Tensor, num_kept: int, return_mask: bool):
+        """mask (uint8, device, length num_edges) -> reference return value (core.py:242-249)."""
+        kept, _, _ = compact_edges(self._ei_dev, mask_dev, num_kept)
+        sparse_data = self.data.clone()
+        sparse_data.edge_index = kept.to(self.device)
+        if return_mask:
+            return sparse_data, mask_dev.cpu().bool()
+        return sparse_data
+
+    def _threshold_mask(self, scores: torch.Tensor, num_keep: int, keep_lowest: bool) -> Tuple[torch.Tensor, int]:
+        """Device keep-mask over `num_edges` positions with the reference's slicing semantics (core.py:232-240)."""
+        nnz = scores.numel()
+        if keep_lowest:
+            take = min(num_keep, nnz)                 # order[:num_keep]
+        elif num_keep == 0:
+            take = nnz                                # order[-0:] is the whole array
+        else:
+            take = min(num_keep, nnz)                 # order[-num_keep:]
+        mask = torch.zeros(self.num_edges, dtype=torch.uint8, device=scores.device)
+        if take > 0:
+            select_mask(scores, take, keep_lowest, out=mask[:nnz])
+        return mask, take
+
+    def sparsify(self, metric: str, retention_ratio: float, return_mask: bool = False, keep_lowest: bool = False):
+        """Keep the top (or bottom) `int(num_edges * retention_ratio)` edges by score (reference core.py:193-249)."""
+        self._check_ratio(retention_ratio)
+        if retention_ratio == 1.0:
+            return self._full(return_mask)
+        scores = self._device_scores(metric)
+        num_keep = int(self.num_edges * retention_ratio)
+        mask, kept = self._threshold_mask(scores, num_keep, keep_lowest)
+        return self._finish(mask, kept, return_mask)
+
+    def sparsify_with_weights(self, metric: str, retention_ratio: float, keep_lowest: bool = False):
+        """Extension: threshold sparsification plus the min-max "-W" edge weights in one device pass.
+
+        Returns (Data, edge_weight float32 on `self.device`, mask). Weight formula: reference
+        scripts/nb05_roman_empire/roman_empire_gpu.py:248-256."""
+        self._check_ratio(retention_ratio)
+        scores = self._device_scores(metric)
+        if retention_ratio == 1.0:
+            mask = torch.ones(self.num_edges, dtype=torch.uint8, device=scores.device)
+            if scores.numel() < self.num_edges:
+                raise IndexError("boolean index did not match indexed array (duplicate edges)")
+            kept = self.num_edges
+        else:
+            mask, kept = self._threshold_mask(scores, int(self.num_edges * retention_ratio), keep_lowest)
+        ei, w, _ = compact_edges(self._ei_dev, mask, kept, scores=scores, with_weights=True, invert_weights=keep_lowest)
+        sparse_data = self.data.clone()
+        sparse_data.edge_index = ei.to(self.device)
+        return sparse_data, w.to(self.device), mask.cpu().bool()
+
+    def sparsify_metric_backbone(self, metric: str, epsilon: float = 1e-9):
+        """Metric-backbone sparsification (reference core.py:251-279) — APSP based, outside the B200 hot path."""
+        raise NotImplementedError(
+            "sparsify_metric_backbone (all-pairs shortest paths, reference metric_backbone.py) is outside the "
+            "edge-scoring hot path this engine accelerates (SURVEY §8f-3); `_scores_to_cost` is provided."
+        )
+
+    def sparsify_sampled(self, metric: str, retention_ratio: float, seed: int = 42, return_mask: bool = False):
+        """Sample edges without replacement with probability proportional to score (reference core.py:281-357)."""
+        self._check_ratio(retention_ratio)
+        if retention_ratio == 1.0:
+            return self._full(return_mask)
+        rng = np.random.default_rng(seed)
+        scores = self.compute_scores(metric)
+        floor = 1e-8
+        scores = np.nan_to_num(scores, nan=floor, posinf=floor, neginf=floor)
+        probs = np.maximum(scores, floor)
+        probs = probs / probs.sum()
+        num_keep = int(self.num_edges * retention_ratio)
+        # NumPy's Generator.choice: PCG64 stream + sequential fp64 cumsum are the reference's observable RNG behaviour
+        selected = rng.choice(self.num_edges, size=num_keep, replace=False, p=probs)
+        mask = np.zeros(self.num_edges, dtype=np.uint8)
+        mask[selected] = 1
+        self.graph  # make sure the device edge list exists
+        mask_dev = torch.from_numpy(mask).to(self._ei_dev.device)
+        return self._finish(mask_dev, num_keep, return_mask)
+
+    def sparsify_degree_aware(self, metric: str, retention_ratio: float, min_edges_per_node: int = 1,
+                              return_mask: bool = False):
+        """Per-node minimum edge budget, then global fill (reference core.py:359-461)."""
+        self._check_ratio(retention_ratio)
+        if retention_ratio == 1.0:
+            return self._full(return_mask)
+        scores = self._device_scores(metric)
+        if scores.numel() < self.num_edges and self.num_edges > 0:
+            # reference: scores[incident_indices] with positions >= nnz (duplicate edges) -> IndexError
+            raise IndexError(f"index {self.num_edges - 1} is out of bounds for axis 0 with size {scores.numel()}")
+        num_keep = int(self.num_edges * retention_ratio)
+        src = self._ei_dev[0]
+        mask, marked = degree_aware_guarantee(src, scores, self.num_nodes, max(int(min_edges_per_node), 0))
+        guaranteed = int(marked.item())            # one 8-byte host read: the output size depends on it
+        kept = guaranteed
+        if guaranteed < num_keep:
+            select_mask(scores, num_keep - guaranteed, keep_lowest=False, exclude=mask, out=mask, or_into=True)
+            kept = num_keep
+        return self._finish(mask, kept, return_mask)
+
+    def get_retention_curve_data(self, metric: str, retention_rates):
+        """reference core.py:463-480."""
+        return [self.sparsify(metric, rate) for rate in retention_rates]
+
+    @property
+    def stats(self) -> dict:
+        """reference core.py:482-490."""
+        return {
+            "num_nodes": self.num_nodes,
+            "num_edges": self.num_edges,
+            "density": self.num_edges / (self.num_nodes * (self.num_nodes - 1)),
+            "avg_degree": self.num_edges / self.num_nodes,
+        }

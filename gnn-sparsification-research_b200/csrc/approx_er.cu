@@ -1,0 +1,354 @@
+// approx_er.cu — approximate effective resistance: JL projection + batched Laplacian CG (K5, K6, K7).
+//
+// Replaces reference src/sparsification/metrics.py:232-298. The reference runs k independent
+// scipy.sparse.linalg.cg solves one after another (k = 2 674 at the Roman-empire shape); here all
+// right-hand sides of a column block advance together: vectors are [n, k] row-major so a CSR row
+// gathers k-contiguous segments of p (256-byte coalesced requests per neighbour), the SpMM is fused
+// with the p.q reduction and the axpy pair with the r.r reduction, and every column keeps SciPy's
+// semantics on its own (x0 = 0; test ||r|| < rtol*||b|| BEFORE each update; at most max_iters updates;
+// a column that stops is frozen while the others continue; ||b|| = 0 -> x = 0).
+//
+// Arithmetic is fp64 with separately rounded multiply/add (SciPy's `x += alpha*p` forms the product
+// first). Row sums inside the SpMM follow csr_matvec's order (neighbours ascending, the diagonal at
+// its sorted position). Column reductions are two-stage and deterministic (fixed block order), so a
+// run is bit-reproducible; they are NOT BLAS ddot's order — ApproxER parity is the 1e-4 relative
+// tolerance BASELINE.json states, not bit equality.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gsp {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / kWarp;
+constexpr int kCheckEvery = 8;  // CG iterations between host reads of the active-column count
+
+struct CgColumns {        // per-column solver state, arrays of length k
+    double* rho;          // r.r at the top of the current iteration
+    double* rho_prev;
+    double* alpha;
+    double* beta;
+    double* atol;
+    int* active;
+    int32_t* iters;
+};
+
+// Y[u, c] = sum over incident undirected edges e (ascending e) of +-R[e, c]   (metrics.py:260-275).
+__global__ void __launch_bounds__(kThreads)
+project_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+               const int32_t* __restrict__ und_id, const double* __restrict__ R, int64_t ldr, int k,
+               double* __restrict__ Y) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    const bool col_ok = c < k;
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    for (int64_t u = warp; u < n; u += nwarps) {
+        double acc = 0.0;
+        const int64_t p0 = indptr[u], p1 = indptr[u + 1];
+        for (int64_t p = p0; p < p1; ++p) {
+            const int32_t e = __ldg(und_id + p);
+            if (e < 0) continue;                                    // self loop / unmatched direction
+            const int32_t v = __ldg(indices + p);
+            if (col_ok) {
+                const double r = __ldg(R + (int64_t)e * ldr + c);
+                acc = (u < v) ? __dadd_rn(acc, r) : __dsub_rn(acc, r);   // +1 * r / -1 * r are exact
+            }
+        }
+        if (col_ok) Y[u * (int64_t)k + c] = acc;
+    }
+}
+
+// Deterministic column reduction helper: every block writes partial[blockIdx.x][c]; warps of a block are
+// combined in fixed order through shared memory.
+__device__ __forceinline__ void block_column_partial(double lane_sum, bool col_ok, int c, int k, double* partial) {
+    __shared__ double sh[kWarps][kWarp];
+    const int w = threadIdx.x >> 5, l = lane_id();
+    sh[w][l] = lane_sum;
+    __syncthreads();
+    if (w == 0 && col_ok) {
+        double s = sh[0][l];
+#pragma unroll
+        for (int i = 1; i < kWarps; ++i) s = __dadd_rn(s, sh[i][l]);
+        partial[(int64_t)blockIdx.x * k + c] = s;
+    }
+}
+
+// r = Y (aliased), x = 0, partial column sums of b^2.
+__global__ void __launch_bounds__(kThreads)
+init_kernel(int64_t n, int k, const double* __restrict__ r, double* __restrict__ x, double* __restrict__ partial) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    const bool col_ok = c < k;
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
+        if (col_ok) {
+            const double b = r[i * (int64_t)k + c];
+            x[i * (int64_t)k + c] = 0.0;
+            s = __dadd_rn(s, __dmul_rn(b, b));
+        }
+    }
+    block_column_partial(s, col_ok, c, k, partial);
+}
+
+// Column finalisation at the TOP of iteration `it`: rr = sum of partials; convergence test; beta.
+__global__ void top_kernel(int k, int nblocks, const double* __restrict__ partial, CgColumns cg, double rtol, int it,
+                           int* __restrict__ num_active) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k) return;
+    double rr = 0.0;
+    for (int b = 0; b < nblocks; ++b) rr = __dadd_rn(rr, partial[(int64_t)b * k + c]);
+    if (it < 0) {  // initialisation: rr = b.b
+        const double bnrm = sqrt(rr);
+        cg.atol[c] = __dmul_rn(rtol, bnrm);                        // atol = max(0, rtol*||b||)
+        cg.rho[c] = rr;
+        cg.rho_prev[c] = 0.0;
+        cg.iters[c] = 0;
+        cg.active[c] = bnrm != 0.0;                                // ||b|| == 0 -> return b (zeros)
+        if (bnrm != 0.0) atomicAdd(num_active, 1);
+        return;
+    }
+    if (!cg.active[c]) return;
+    if (it > 0) {
+        cg.rho_prev[c] = cg.rho[c];
+        cg.rho[c] = rr;
+    }
+    if (sqrt(rr) < cg.atol[c]) {                                   // "Are we done?" before the update
+        cg.active[c] = 0;
+        atomicSub(num_active, 1);
+        return;
+    }
+    cg.beta[c] = it > 0 ? __ddiv_rn(rr, cg.rho_prev[c]) : 0.0;
+}
+
+// p = r + beta * p   (first iteration: p = r)
+__global__ void __launch_bounds__(kThreads)
+direction_kernel(int64_t n, int k, const double* __restrict__ r, double* __restrict__ p, CgColumns cg, int it) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    if (c >= k || !cg.active[c]) return;
+    const double beta = cg.beta[c];
+    for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
+        const int64_t o = i * (int64_t)k + c;
+        p[o] = it > 0 ? __dadd_rn(__dmul_rn(p[o], beta), r[o]) : r[o];
+    }
+}
+
+// q = (D - A + reg I) p for a 32-column strip, fused with the p.q column partials.
+__global__ void __launch_bounds__(kThreads)
+spmm_dot_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const double* __restrict__ data, const double* __restrict__ diag, int k, const double* __restrict__ p,
+                double* __restrict__ q, const int* __restrict__ active, double* __restrict__ partial) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    const bool col_ok = c < k && active[c];
+    double dot = 0.0;
+    // a strip whose 32 columns have all stopped does no work (uniform per warp)
+    if (__any_sync(0xffffffffu, col_ok)) {
+        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
+            const int64_t p0 = indptr[i], p1 = indptr[i + 1];
+            const double pi = col_ok ? p[i * (int64_t)k + c] : 0.0;
+            const double dterm = __dmul_rn(diag[i], pi);
+            double s = 0.0;
+            bool placed = false;
+            for (int64_t t = p0; t < p1; ++t) {
+                const int32_t j = __ldg(indices + t);
+                if (j == i) {                    // self loop: folded into diag (L_ii = deg - a_ii + reg)
+                    s = __dadd_rn(s, dterm);
+                    placed = true;
+                    continue;
+                }
+                if (!placed && j > i) {
+                    s = __dadd_rn(s, dterm);
+                    placed = true;
+                }
+                if (col_ok) {
+                    const double pj = __ldg(p + (int64_t)j * k + c);
+                    s = data ? __dadd_rn(s, __dmul_rn(-__ldg(data + t), pj)) : __dsub_rn(s, pj);
+                }
+            }
+            if (!placed) s = __dadd_rn(s, dterm);
+            if (col_ok) {
+                q[i * (int64_t)k + c] = s;
+                dot = __dadd_rn(dot, __dmul_rn(pi, s));
+            }
+        }
+    }
+    block_column_partial(dot, c < k, c, k, partial);
+}
+
+__global__ void alpha_kernel(int k, int nblocks, const double* __restrict__ partial, CgColumns cg) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= k || !cg.active[c]) return;
+    double pq = 0.0;
+    for (int b = 0; b < nblocks; ++b) pq = __dadd_rn(pq, partial[(int64_t)b * k + c]);
+    cg.alpha[c] = __ddiv_rn(cg.rho[c], pq);
+    cg.iters[c] += 1;
+}
+
+// x += alpha p ; r -= alpha q ; partial column sums of the new r.r
+__global__ void __launch_bounds__(kThreads)
+update_kernel(int64_t n, int k, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+              double* __restrict__ r, CgColumns cg, double* __restrict__ partial) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    const bool col_ok = c < k && cg.active[c];
+    double s = 0.0;
+    if (col_ok) {
+        const double alpha = cg.alpha[c];
+        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
+            const int64_t o = i * (int64_t)k + c;
+            x[o] = __dadd_rn(x[o], __dmul_rn(alpha, p[o]));
+            const double rn = __dsub_rn(r[o], __dmul_rn(alpha, q[o]));
+            r[o] = rn;
+            s = __dadd_rn(s, __dmul_rn(rn, rn));
+        }
+    }
+    block_column_partial(s, c < k, c, k, partial);
+}
+
+__global__ void diag_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const double* __restrict__ data, double reg, double* __restrict__ diag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double deg = 0.0, self = 0.0;
+        for (int64_t t = indptr[i]; t < indptr[i + 1]; ++t) {
+            const double a = data ? data[t] : 1.0;
+            deg = __dadd_rn(deg, a);
+            if (indices[t] == i) self = a;
+        }
+        diag[i] = __dadd_rn(__dsub_rn(deg, self), reg);  // (D - A)_ii + 1e-6  (metrics.py:251-256)
+    }
+}
+
+// partial[e] = sum_c (Z[u,c] - Z[v,c])^2 ; non-finite solver output counts as 0 (metrics.py:287-293)
+__global__ void __launch_bounds__(kThreads)
+resistance_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ rows, const int32_t* __restrict__ indices,
+                  const double* __restrict__ z, int k, double* __restrict__ out) {
+    const int lane = lane_id();
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+    for (int64_t e = e_begin + warp; e < e_end; e += nwarps) {
+        const double* zu = z + (int64_t)__ldg(rows + e) * k;
+        const double* zv = z + (int64_t)__ldg(indices + e) * k;
+        double s = 0.0;
+        for (int c = lane; c < k; c += kWarp) {
+            double a = __ldg(zu + c), b = __ldg(zv + c);
+            if (!isfinite(a)) a = 0.0;
+            if (!isfinite(b)) b = 0.0;
+            const double d = __dsub_rn(a, b);
+            s = __dadd_rn(s, __dmul_rn(d, d));
+        }
+        for (int o = 16; o; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) out[e - e_begin] = s;
+    }
+}
+
+__global__ void er_finalize_kernel(int64_t n, double* s) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = s[i];
+        if (!isfinite(v)) v = 1e-10;          // nan_to_num(nan=1e-10, posinf=1e-10, neginf=1e-10)
+        s[i] = v > 1e-10 ? v : 1e-10;         // np.maximum(r_eff, 1e-10)
+    }
+}
+
+std::mutex g_und_mutex;
+
+int ensure_und_id(Graph* g, void* stream) {
+    std::lock_guard<std::mutex> lock(g_und_mutex);
+    if (g->und_id || g->nnz == 0) return GSP_OK;
+    int32_t* buf = nullptr;
+    GSP_CUDA_TRY(cudaMalloc(&buf, (size_t)g->nnz * sizeof(int32_t)));
+    int rc = gsp_graph_undirected_ids(reinterpret_cast<gsp_graph*>(g), buf, stream);
+    if (rc) {
+        cudaFree(buf);
+        return rc;
+    }
+    g->und_id = buf;
+    return GSP_OK;
+}
+
+}  // namespace
+}  // namespace gsp
+
+using namespace gsp;
+
+GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_t ldr, int32_t k, int32_t max_iters,
+                                  double rtol, double reg, int64_t e_begin, int64_t e_end, double* d_partial,
+                                  int32_t* d_iters, void* stream) {
+    GSP_REQUIRE(gg != nullptr, "graph is NULL");
+    Graph* g = const_cast<Graph*>(reinterpret_cast<const Graph*>(gg));
+    GSP_REQUIRE(e_begin >= 0 && e_begin <= e_end && e_end <= g->nnz, "edge range outside [0, nnz]");
+    GSP_REQUIRE(k >= 1 && max_iters >= 0 && ldr >= k, "bad k / max_iters / ldr");
+    GSP_REQUIRE(d_R && (e_end == e_begin || d_partial), "NULL argument");
+    if (!g->symmetric) {
+        set_error("approximate effective resistance needs a symmetric adjacency pattern (reference metrics.py:208-209)");
+        return GSP_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int64_t n = g->n;
+    if (int rc = ensure_und_id(g, stream)) return rc;
+
+    const int strips = (k + kWarp - 1) / kWarp;
+    // row blocks: enough CTAs for >= 8 per SM over all strips, at most one warp-row each
+    int64_t row_blocks = (static_cast<int64_t>(kNumSMs) * 8 + strips - 1) / strips;
+    const int64_t max_rb = (n + kWarps - 1) / kWarps;
+    if (row_blocks > max_rb) row_blocks = max_rb;
+    if (row_blocks < 1) row_blocks = 1;
+    const dim3 grid2d((unsigned)row_blocks, (unsigned)strips);
+    const int nb = (int)row_blocks;
+
+    const size_t vec = (size_t)n * (size_t)k;
+    Scratch<double> x, r, p, q, partial, diag, cols;
+    Scratch<int> flags;
+    Scratch<int32_t> iters_local;
+    GSP_CUDA_TRY(x.alloc(vec, s));
+    GSP_CUDA_TRY(r.alloc(vec, s));
+    GSP_CUDA_TRY(p.alloc(vec, s));
+    GSP_CUDA_TRY(q.alloc(vec, s));
+    GSP_CUDA_TRY(partial.alloc((size_t)nb * k, s));
+    GSP_CUDA_TRY(diag.alloc(n, s));
+    GSP_CUDA_TRY(cols.alloc((size_t)5 * k, s));
+    GSP_CUDA_TRY(flags.alloc((size_t)k + 1, s));
+    GSP_CUDA_TRY(iters_local.alloc(k, s));
+    CgColumns cg{cols.ptr, cols.ptr + k, cols.ptr + 2 * (size_t)k, cols.ptr + 3 * (size_t)k, cols.ptr + 4 * (size_t)k,
+                 flags.ptr, d_iters ? d_iters : iters_local.ptr};
+    int* num_active = flags.ptr + k;
+    GSP_CUDA_TRY(cudaMemsetAsync(num_active, 0, sizeof(int), s));
+
+    diag_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, g->indptr, g->indices, g->data, reg, diag.ptr);
+    GSP_CHECK_LAUNCH();
+    project_kernel<<<grid2d, kThreads, 0, s>>>(n, g->indptr, g->indices, g->und_id, d_R, ldr, k, r.ptr);
+    GSP_CHECK_LAUNCH();
+    init_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, x.ptr, partial.ptr);
+    GSP_CHECK_LAUNCH();
+    const int col_blocks = (k + 127) / 128;
+    top_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg, rtol, -1, num_active);
+    GSP_CHECK_LAUNCH();
+
+    int host_active = 1;
+    for (int it = 0; it < max_iters; ++it) {
+        if (it % kCheckEvery == 0) {  // the only host round trip of the solve
+            GSP_CUDA_TRY(cudaMemcpyAsync(&host_active, num_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+            GSP_CUDA_TRY(cudaStreamSynchronize(s));
+            if (host_active <= 0) break;
+        }
+        top_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg, rtol, it, num_active);
+        direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
+        spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(n, g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, cg.active,
+                                                   partial.ptr);
+        alpha_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg);
+        update_kernel<<<grid2d, kThreads, 0, s>>>(n, k, p.ptr, q.ptr, x.ptr, r.ptr, cg, partial.ptr);
+        GSP_CHECK_LAUNCH();
+    }
+    if (e_end > e_begin) {
+        const int64_t edges = e_end - e_begin;
+        resistance_kernel<<<grid_for(edges, kWarps, 8), kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, x.ptr, k,
+                                                                         d_partial);
+        GSP_CHECK_LAUNCH();
+    }
+    return GSP_OK;
+}
+
+GSP_API int gsp_er_finalize(double* d_score, int64_t count, void* stream) {
+    GSP_REQUIRE(count >= 0 && (count == 0 || d_score), "bad arguments");
+    if (count == 0) return GSP_OK;
+    er_finalize_kernel<<<grid_for(count, 256), 256, 0, as_stream(stream)>>>(count, d_score);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}

@@ -1,0 +1,103 @@
+// common.cuh — shared helpers for libgsp.so (sm_100a). Internal; the public surface is include/gsp.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/gsp.h"
+
+#define GSP_API extern "C" __attribute__((visibility("default")))
+
+namespace gsp {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kWarp = 32;
+
+void set_error(const char* fmt, ...);
+
+#define GSP_CUDA_TRY(expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            gsp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GSP_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)
+
+#define GSP_REQUIRE(cond, msg)                                  \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            gsp::set_error("invalid argument: %s", msg);        \
+            return GSP_ERR_INVALID;                             \
+        }                                                       \
+    } while (0)
+
+#define GSP_CHECK_LAUNCH() GSP_CUDA_TRY(cudaGetLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Stream-ordered scratch buffer (cudaMallocAsync pool): freed on the same stream when it goes out of scope.
+template <typename T>
+struct Scratch {
+    T* ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc(size_t count, cudaStream_t s) {
+        stream = s;
+        return cudaMallocAsync(reinterpret_cast<void**>(&ptr), (count ? count : 1) * sizeof(T), s);
+    }
+    ~Scratch() {
+        if (ptr) cudaFreeAsync(ptr, stream);
+    }
+    Scratch() = default;
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+};
+
+// Library-owned canonical graph. Everything lives on `device`.
+struct Graph {
+    int device = 0;
+    int64_t n = 0;
+    int64_t num_input_edges = 0;
+    int64_t nnz = 0;
+    int64_t num_undirected = 0;
+    int64_t max_degree = 0;
+    double sum_degree_sq = 0.0;
+    bool symmetric = false;
+    bool input_canonical = false;
+    bool unit_weights = true;
+    int64_t* indptr = nullptr;   // [n+1]
+    int32_t* indices = nullptr;  // [nnz] column ids, ascending inside a row
+    int32_t* rows = nullptr;     // [nnz] row id per canonical position
+    double* data = nullptr;      // [nnz] merged values (multiplicities); nullptr when unit_weights
+    // transpose pattern (only when !symmetric): row v of A^T == column v of A
+    int64_t* tptr = nullptr;
+    int32_t* tidx = nullptr;
+    // lazily built
+    int32_t* und_id = nullptr;   // [nnz]
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// 128-bit read-only streaming load of four int32 (index lists are consumed once per intersection).
+__device__ __forceinline__ int4 ldg_int4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
+
+// Order-preserving map fp64 -> uint64 (ascending). -0.0 and +0.0 are made equal first because IEEE
+// comparison (what argsort uses) treats them as ties.
+__device__ __forceinline__ uint64_t ordered_key(double s) {
+    if (s == 0.0) s = 0.0;
+    uint64_t b = static_cast<uint64_t>(__double_as_longlong(s));
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks_per_sm = 16) {
+    int64_t blocks = (work_items + per_block - 1) / per_block;
+    int64_t cap = static_cast<int64_t>(kNumSMs) * max_blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<int>(blocks);
+}
+
+}  // namespace gsp

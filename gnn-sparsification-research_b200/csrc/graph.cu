@@ -1,0 +1,476 @@
+// graph.cu — canonical CSR construction on the device (kernel family K1).
+//
+// Replaces reference src/sparsification/core.py:70-74, `sp.csr_matrix((ones(E), (row, col)))`:
+// rows ascending, columns ascending in a row, duplicates merged with their values summed
+// (SURVEY App. A.7). PyG datasets arrive already coalesced, so the common case is a single
+// validation pass plus a narrowing copy (int64 -> int32 columns); otherwise the edge list is
+// radix-sorted on a packed (row, col) key. The sort/scan primitives here come from CUB (CUDA
+// toolkit header library) — graph construction is outside the scoring/selection hot path that
+// BASELINE.json's north_star names; every scoring and selection kernel is hand-written.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <mutex>
+#include <new>
+
+#include "common.cuh"
+
+namespace gsp {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct CheckFlags {
+    int out_of_range;
+    int not_canonical;
+    int non_unit;
+    int has_zero;
+};
+
+__global__ void check_edges_kernel(int64_t n, int64_t E, const int64_t* __restrict__ row,
+                                   const int64_t* __restrict__ col, const double* __restrict__ val,
+                                   CheckFlags* flags) {
+    int bad_range = 0, bad_order = 0, non_unit = 0, zero = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = row[e], c = col[e];
+        if (r < 0 || r >= n || c < 0 || c >= n) bad_range = 1;
+        if (e > 0) {
+            int64_t pr = row[e - 1], pc = col[e - 1];
+            if (pr > r || (pr == r && pc >= c)) bad_order = 1;
+        }
+        if (val) {
+            double v = val[e];
+            if (v != 1.0) non_unit = 1;
+            if (v == 0.0) zero = 1;
+        }
+    }
+    if (__any_sync(0xffffffffu, bad_range) && lane_id() == 0) atomicOr(&flags->out_of_range, 1);
+    if (__any_sync(0xffffffffu, bad_order) && lane_id() == 0) atomicOr(&flags->not_canonical, 1);
+    if (__any_sync(0xffffffffu, non_unit) && lane_id() == 0) atomicOr(&flags->non_unit, 1);
+    if (__any_sync(0xffffffffu, zero) && lane_id() == 0) atomicOr(&flags->has_zero, 1);
+}
+
+// Canonical input: narrow the columns/rows to int32 and keep the values.
+__global__ void narrow_kernel(int64_t E, const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                              const double* __restrict__ val, int32_t* __restrict__ rows_out,
+                              int32_t* __restrict__ idx_out, double* __restrict__ data_out) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        rows_out[e] = (int32_t)row[e];
+        idx_out[e] = (int32_t)col[e];
+        if (data_out) data_out[e] = val[e];
+    }
+}
+
+// indptr from a row-sorted row-id array: position e is the start of every row in (rows[e-1], rows[e]].
+__global__ void row_bounds_kernel(int64_t n, int64_t nnz, const int32_t* __restrict__ rows, int64_t* __restrict__ indptr) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e <= nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t prev = (e == 0) ? -1 : rows[e - 1];
+        int64_t cur = (e == nnz) ? n : rows[e];
+        for (int64_t r = prev + 1; r <= cur; ++r) indptr[r] = e;
+    }
+}
+
+__global__ void pack_keys_kernel(int64_t E, const int64_t* __restrict__ major, const int64_t* __restrict__ minor,
+                                 int shift, uint64_t* __restrict__ keys) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        keys[e] = ((uint64_t)major[e] << shift) | (uint64_t)minor[e];
+}
+
+__global__ void pack_keys32_kernel(int64_t E, const int32_t* __restrict__ major, const int32_t* __restrict__ minor,
+                                   int shift, uint64_t* __restrict__ keys) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        keys[e] = ((uint64_t)(uint32_t)major[e] << shift) | (uint64_t)(uint32_t)minor[e];
+}
+
+__global__ void head_flags_kernel(int64_t E, const uint64_t* __restrict__ keys, int64_t* __restrict__ flags) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        flags[e] = (e == 0 || keys[e] != keys[e - 1]) ? 1 : 0;
+}
+
+// One thread per run head: write the merged entry, summing the run's values in sorted (input) order.
+__global__ void merge_runs_kernel(int64_t E, const uint64_t* __restrict__ keys, const int64_t* __restrict__ pos_incl,
+                                  const double* __restrict__ val, int shift, int32_t* __restrict__ rows_out,
+                                  int32_t* __restrict__ idx_out, double* __restrict__ data_out) {
+    const uint64_t low_mask = (shift == 64) ? ~0ull : ((1ull << shift) - 1ull);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t k = keys[e];
+        if (e > 0 && keys[e - 1] == k) continue;
+        int64_t p = pos_incl[e] - 1;
+        double s = 0.0;
+        for (int64_t j = e; j < E && keys[j] == k; ++j) s += val ? val[j] : 1.0;
+        rows_out[p] = (int32_t)(k >> shift);
+        idx_out[p] = (int32_t)(k & low_mask);
+        data_out[p] = s;
+    }
+}
+
+__global__ void unpack_minor_kernel(int64_t E, const uint64_t* __restrict__ keys, int shift, int32_t* __restrict__ major_out,
+                                    int32_t* __restrict__ minor_out) {
+    const uint64_t low_mask = (1ull << shift) - 1ull;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        if (major_out) major_out[e] = (int32_t)(keys[e] >> shift);
+        minor_out[e] = (int32_t)(keys[e] & low_mask);
+    }
+}
+
+struct GraphStats {
+    unsigned long long max_degree;
+    double sum_degree_sq;
+    unsigned long long num_undirected;
+    int asymmetric;
+    int non_unit;
+    int has_zero;
+};
+
+__global__ void degree_stats_kernel(int64_t n, const int64_t* __restrict__ indptr, GraphStats* st) {
+    unsigned long long mx = 0;
+    double s2 = 0.0;
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long d = (unsigned long long)(indptr[u + 1] - indptr[u]);
+        mx = d > mx ? d : mx;
+        s2 += (double)d * (double)d;
+    }
+    for (int o = 16; o; o >>= 1) {
+        unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane_id() == 0) {
+        atomicMax(&st->max_degree, mx);
+        atomicAdd(&st->sum_degree_sq, s2);
+    }
+}
+
+// Pattern symmetry + undirected count + value flags in one pass over the canonical entries.
+__global__ void edge_stats_kernel(int64_t nnz, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                  const int32_t* __restrict__ rows, const double* __restrict__ data, GraphStats* st) {
+    unsigned long long und = 0;
+    int asym = 0, non_unit = 0, zero = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int32_t u = rows[e], v = indices[e];
+        und += (u < v);
+        if (u != v) {  // look for (v, u)
+            int64_t lo = indptr[v], hi = indptr[v + 1];
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (indices[mid] < u) lo = mid + 1; else hi = mid;
+            }
+            if (!(lo < indptr[v + 1] && indices[lo] == u)) asym = 1;
+        }
+        if (data) {
+            double x = data[e];
+            if (x != 1.0) non_unit = 1;
+            if (x == 0.0) zero = 1;
+        }
+    }
+    for (int o = 16; o; o >>= 1) und += __shfl_xor_sync(0xffffffffu, und, o);
+    if (lane_id() == 0 && und) atomicAdd(&st->num_undirected, und);
+    if (__any_sync(0xffffffffu, asym) && lane_id() == 0) atomicOr(&st->asymmetric, 1);
+    if (__any_sync(0xffffffffu, non_unit) && lane_id() == 0) atomicOr(&st->non_unit, 1);
+    if (__any_sync(0xffffffffu, zero) && lane_id() == 0) atomicOr(&st->has_zero, 1);
+}
+
+__global__ void degrees_kernel(int64_t n, const int64_t* __restrict__ indptr, int32_t* __restrict__ deg) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x)
+        deg[u] = (int32_t)(indptr[u + 1] - indptr[u]);
+}
+
+// und_id: exclusive rank of row<col entries, mirrored to the (col,row) direction.
+__global__ void upper_flags_kernel(int64_t nnz, const int32_t* __restrict__ rows, const int32_t* __restrict__ indices,
+                                   int64_t* __restrict__ flags) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+        flags[e] = rows[e] < indices[e] ? 1 : 0;
+}
+
+__global__ void und_id_kernel(int64_t nnz, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                              const int32_t* __restrict__ rows, const int64_t* __restrict__ rank_incl,
+                              int32_t* __restrict__ und_id) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        int32_t u = rows[e], v = indices[e];
+        if (u < v) {
+            und_id[e] = (int32_t)(rank_incl[e] - 1);
+        } else if (u == v) {
+            und_id[e] = -1;
+        } else {  // find (v, u), v < u
+            int64_t lo = indptr[v], hi = indptr[v + 1];
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (indices[mid] < u) lo = mid + 1; else hi = mid;
+            }
+            und_id[e] = (lo < indptr[v + 1] && indices[lo] == u) ? (int32_t)(rank_incl[lo] - 1) : -1;
+        }
+    }
+}
+
+__global__ void fill_ones_kernel(int64_t n, double* out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = 1.0;
+}
+
+int bits_for(int64_t n) {
+    int b = 1;
+    while ((1ll << b) < n) ++b;
+    return b;
+}
+
+void free_graph(Graph* g) {
+    if (!g) return;
+    cudaFree(g->indptr);
+    cudaFree(g->indices);
+    cudaFree(g->rows);
+    cudaFree(g->data);
+    cudaFree(g->tptr);
+    cudaFree(g->tidx);
+    cudaFree(g->und_id);
+    delete g;
+}
+
+// Sort a packed-key edge list; returns the sorted keys (and values) in freshly allocated scratch.
+int sort_keys(uint64_t* keys_in, uint64_t* keys_out, const double* val_in, double* val_out, int64_t E, int end_bit,
+              cudaStream_t s) {
+    size_t tmp_bytes = 0;
+    if (val_in) {
+        GSP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, val_in, val_out, E, 0, end_bit, s));
+    } else {
+        GSP_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_in, keys_out, E, 0, end_bit, s));
+    }
+    Scratch<char> tmp;
+    GSP_CUDA_TRY(tmp.alloc(tmp_bytes, s));
+    if (val_in) {
+        GSP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys_in, keys_out, val_in, val_out, E, 0, end_bit, s));
+    } else {
+        GSP_CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp.ptr, tmp_bytes, keys_in, keys_out, E, 0, end_bit, s));
+    }
+    return GSP_OK;
+}
+
+int inclusive_sum(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s) {
+    size_t tmp_bytes = 0;
+    GSP_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, in, out, count, s));
+    Scratch<char> tmp;
+    GSP_CUDA_TRY(tmp.alloc(tmp_bytes, s));
+    GSP_CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp.ptr, tmp_bytes, in, out, count, s));
+    return GSP_OK;
+}
+
+int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int64_t* d_col, const double* d_val,
+                cudaStream_t s) {
+    const int threads = 256;
+    const int grid = grid_for(E, threads);
+    g->n = n;
+    g->num_input_edges = E;
+
+    Scratch<CheckFlags> flags;
+    GSP_CUDA_TRY(flags.alloc(1, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(flags.ptr, 0, sizeof(CheckFlags), s));
+    if (E > 0) {
+        check_edges_kernel<<<grid, threads, 0, s>>>(n, E, d_row, d_col, d_val, flags.ptr);
+        GSP_CHECK_LAUNCH();
+    }
+    CheckFlags hf;
+    GSP_CUDA_TRY(cudaMemcpyAsync(&hf, flags.ptr, sizeof(hf), cudaMemcpyDeviceToHost, s));
+    GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    if (hf.out_of_range) {
+        set_error("edge_index holds a node id outside [0, %lld)", (long long)n);
+        return GSP_ERR_INVALID;
+    }
+    g->input_canonical = !hf.not_canonical && !hf.has_zero;
+    const bool keep_values = d_val && hf.non_unit;
+
+    GSP_CUDA_TRY(cudaMalloc(&g->indptr, (size_t)(n + 1) * sizeof(int64_t)));
+    if (g->input_canonical) {
+        g->nnz = E;
+        GSP_CUDA_TRY(cudaMalloc(&g->indices, (size_t)(E ? E : 1) * sizeof(int32_t)));
+        GSP_CUDA_TRY(cudaMalloc(&g->rows, (size_t)(E ? E : 1) * sizeof(int32_t)));
+        if (keep_values) GSP_CUDA_TRY(cudaMalloc(&g->data, (size_t)(E ? E : 1) * sizeof(double)));
+        if (E > 0) {
+            narrow_kernel<<<grid, threads, 0, s>>>(E, d_row, d_col, d_val, g->rows, g->indices, g->data);
+            GSP_CHECK_LAUNCH();
+        }
+    } else {
+        const int shift = bits_for(n);
+        Scratch<uint64_t> keys, keys_sorted;
+        Scratch<double> val_sorted;
+        Scratch<int64_t> heads, pos;
+        GSP_CUDA_TRY(keys.alloc(E, s));
+        GSP_CUDA_TRY(keys_sorted.alloc(E, s));
+        GSP_CUDA_TRY(heads.alloc(E, s));
+        GSP_CUDA_TRY(pos.alloc(E, s));
+        if (d_val) GSP_CUDA_TRY(val_sorted.alloc(E, s));
+        pack_keys_kernel<<<grid, threads, 0, s>>>(E, d_row, d_col, shift, keys.ptr);
+        GSP_CHECK_LAUNCH();
+        int rc = sort_keys(keys.ptr, keys_sorted.ptr, d_val, val_sorted.ptr, E, 2 * shift, s);
+        if (rc) return rc;
+        head_flags_kernel<<<grid, threads, 0, s>>>(E, keys_sorted.ptr, heads.ptr);
+        GSP_CHECK_LAUNCH();
+        rc = inclusive_sum(heads.ptr, pos.ptr, E, s);
+        if (rc) return rc;
+        int64_t nnz = 0;
+        GSP_CUDA_TRY(cudaMemcpyAsync(&nnz, pos.ptr + (E - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        GSP_CUDA_TRY(cudaStreamSynchronize(s));
+        g->nnz = nnz;
+        GSP_CUDA_TRY(cudaMalloc(&g->indices, (size_t)nnz * sizeof(int32_t)));
+        GSP_CUDA_TRY(cudaMalloc(&g->rows, (size_t)nnz * sizeof(int32_t)));
+        GSP_CUDA_TRY(cudaMalloc(&g->data, (size_t)nnz * sizeof(double)));
+        merge_runs_kernel<<<grid, threads, 0, s>>>(E, keys_sorted.ptr, pos.ptr, d_val ? val_sorted.ptr : nullptr, shift,
+                                                   g->rows, g->indices, g->data);
+        GSP_CHECK_LAUNCH();
+    }
+    row_bounds_kernel<<<grid_for(g->nnz + 1, threads), threads, 0, s>>>(n, g->nnz, g->rows, g->indptr);
+    GSP_CHECK_LAUNCH();
+
+    Scratch<GraphStats> stats;
+    GSP_CUDA_TRY(stats.alloc(1, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(stats.ptr, 0, sizeof(GraphStats), s));
+    degree_stats_kernel<<<grid_for(n, threads), threads, 0, s>>>(n, g->indptr, stats.ptr);
+    GSP_CHECK_LAUNCH();
+    if (g->nnz > 0) {
+        edge_stats_kernel<<<grid_for(g->nnz, threads), threads, 0, s>>>(g->nnz, g->indptr, g->indices, g->rows, g->data,
+                                                                        stats.ptr);
+        GSP_CHECK_LAUNCH();
+    }
+    GraphStats hs;
+    GSP_CUDA_TRY(cudaMemcpyAsync(&hs, stats.ptr, sizeof(hs), cudaMemcpyDeviceToHost, s));
+    GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    if (hs.has_zero) {
+        set_error("merged adjacency holds explicit zeros; drop them before building the graph");
+        return GSP_ERR_UNSUPPORTED;
+    }
+    g->max_degree = (int64_t)hs.max_degree;
+    g->sum_degree_sq = hs.sum_degree_sq;
+    g->num_undirected = (int64_t)hs.num_undirected;
+    g->symmetric = !hs.asymmetric;
+    g->unit_weights = !(g->data && hs.non_unit);
+    if (g->data && g->unit_weights) {  // multiplicities all 1: no need to keep 8*nnz bytes around
+        GSP_CUDA_TRY(cudaFree(g->data));
+        g->data = nullptr;
+    }
+
+    if (!g->symmetric) {  // column lists for Jaccard's row(u) ∩ col(v): CSR of the transposed pattern
+        const int shift = bits_for(n);
+        const int64_t nnz = g->nnz;
+        Scratch<uint64_t> keys, keys_sorted;
+        Scratch<int32_t> trow;
+        GSP_CUDA_TRY(keys.alloc(nnz, s));
+        GSP_CUDA_TRY(keys_sorted.alloc(nnz, s));
+        GSP_CUDA_TRY(trow.alloc(nnz, s));
+        GSP_CUDA_TRY(cudaMalloc(&g->tptr, (size_t)(n + 1) * sizeof(int64_t)));
+        GSP_CUDA_TRY(cudaMalloc(&g->tidx, (size_t)nnz * sizeof(int32_t)));
+        pack_keys32_kernel<<<grid_for(nnz, threads), threads, 0, s>>>(nnz, g->indices, g->rows, shift, keys.ptr);
+        GSP_CHECK_LAUNCH();
+        int rc = sort_keys(keys.ptr, keys_sorted.ptr, nullptr, nullptr, nnz, 2 * shift, s);
+        if (rc) return rc;
+        unpack_minor_kernel<<<grid_for(nnz, threads), threads, 0, s>>>(nnz, keys_sorted.ptr, shift, trow.ptr, g->tidx);
+        GSP_CHECK_LAUNCH();
+        row_bounds_kernel<<<grid_for(nnz + 1, threads), threads, 0, s>>>(n, nnz, trow.ptr, g->tptr);
+        GSP_CHECK_LAUNCH();
+        GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return GSP_OK;
+}
+
+}  // namespace
+}  // namespace gsp
+
+using namespace gsp;
+
+GSP_API int gsp_version(void) { return GSP_VERSION; }
+
+GSP_API const char* gsp_last_error(void) { return gsp::g_error; }
+
+GSP_API int gsp_graph_create(int64_t num_nodes, int64_t num_edges, const int64_t* d_row, const int64_t* d_col,
+                             const double* d_val, void* stream, gsp_graph** out) {
+    GSP_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    GSP_REQUIRE(num_nodes >= 0 && num_nodes < (1ll << 31), "num_nodes must be in [0, 2^31)");
+    GSP_REQUIRE(num_edges >= 0, "num_edges must be >= 0");
+    GSP_REQUIRE(num_edges == 0 || (d_row && d_col), "edge pointers are NULL");
+    Graph* g = new (std::nothrow) Graph();
+    if (!g) {
+        set_error("out of host memory");
+        return GSP_ERR_NOMEM;
+    }
+    if (cudaGetDevice(&g->device) != cudaSuccess) {
+        set_error("no CUDA device available: %s", cudaGetErrorString(cudaGetLastError()));
+        delete g;
+        return GSP_ERR_CUDA;
+    }
+    int rc = build_graph(g, num_nodes, num_edges, d_row, d_col, d_val, as_stream(stream));
+    if (rc != GSP_OK) {
+        free_graph(g);
+        return rc;
+    }
+    *out = reinterpret_cast<gsp_graph*>(g);
+    return GSP_OK;
+}
+
+GSP_API void gsp_graph_destroy(gsp_graph* g) { free_graph(reinterpret_cast<Graph*>(g)); }
+
+GSP_API int gsp_graph_get_info(const gsp_graph* gg, gsp_graph_info* out) {
+    GSP_REQUIRE(gg && out, "NULL argument");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    out->num_nodes = g->n;
+    out->num_input_edges = g->num_input_edges;
+    out->nnz = g->nnz;
+    out->num_undirected = g->num_undirected;
+    out->max_degree = g->max_degree;
+    out->sum_degree_sq = g->sum_degree_sq;
+    out->symmetric = g->symmetric;
+    out->input_canonical = g->input_canonical;
+    out->unit_weights = g->unit_weights;
+    out->device = g->device;
+    return GSP_OK;
+}
+
+GSP_API int gsp_graph_export(const gsp_graph* gg, int64_t* d_indptr, int32_t* d_indices, double* d_data, int32_t* d_rows,
+                             void* stream) {
+    GSP_REQUIRE(gg, "graph is NULL");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    cudaStream_t s = as_stream(stream);
+    if (d_indptr) GSP_CUDA_TRY(cudaMemcpyAsync(d_indptr, g->indptr, (size_t)(g->n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    if (d_indices && g->nnz) GSP_CUDA_TRY(cudaMemcpyAsync(d_indices, g->indices, (size_t)g->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_rows && g->nnz) GSP_CUDA_TRY(cudaMemcpyAsync(d_rows, g->rows, (size_t)g->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_data && g->nnz) {
+        if (g->data) {
+            GSP_CUDA_TRY(cudaMemcpyAsync(d_data, g->data, (size_t)g->nnz * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        } else {
+            fill_ones_kernel<<<grid_for(g->nnz, 256), 256, 0, s>>>(g->nnz, d_data);
+            GSP_CHECK_LAUNCH();
+        }
+    }
+    return GSP_OK;
+}
+
+GSP_API int gsp_graph_degrees(const gsp_graph* gg, int32_t* d_deg, void* stream) {
+    GSP_REQUIRE(gg && d_deg, "NULL argument");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (g->n == 0) return GSP_OK;
+    degrees_kernel<<<grid_for(g->n, 256), 256, 0, as_stream(stream)>>>(g->n, g->indptr, d_deg);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_graph_undirected_ids(const gsp_graph* gg, int32_t* d_uid, void* stream) {
+    GSP_REQUIRE(gg && d_uid, "NULL argument");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (g->nnz == 0) return GSP_OK;
+    cudaStream_t s = as_stream(stream);
+    Scratch<int64_t> flags, rank;
+    GSP_CUDA_TRY(flags.alloc(g->nnz, s));
+    GSP_CUDA_TRY(rank.alloc(g->nnz, s));
+    const int grid = grid_for(g->nnz, 256);
+    upper_flags_kernel<<<grid, 256, 0, s>>>(g->nnz, g->rows, g->indices, flags.ptr);
+    GSP_CHECK_LAUNCH();
+    int rc = inclusive_sum(flags.ptr, rank.ptr, g->nnz, s);
+    if (rc) return rc;
+    und_id_kernel<<<grid, 256, 0, s>>>(g->nnz, g->indptr, g->indices, g->rows, rank.ptr, d_uid);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}

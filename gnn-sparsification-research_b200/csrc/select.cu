@@ -1,0 +1,519 @@
+// select.cu — global top-k / bottom-k edge selection, degree-aware guarantee, compaction (K8, K9, K10).
+//
+// Replaces the full `np.argsort(scores)` of reference src/sparsification/core.py:232-240 (threshold /
+// inverse-threshold), :421-451 (degree-aware) and the boolean-mask gather `edge_index[:, mask]` (:242) plus the
+// "-W" weights of scripts/nb05_roman_empire/roman_empire_gpu.py:248-256.
+//
+// Selection is an MSB-first radix select on order-preserving 64-bit keys: 6 histogram passes (11,11,11,11,11,9
+// bits) find the key t of the num_keep-th element and how many members of its tie class are needed; one counting
+// pass and one writing pass then resolve ties by POSITION so the result equals a stable argsort:
+// top-k keeps the highest positions of the tie class, bottom-k the lowest. No sort, no host synchronisation; the
+// 16 KB histograms are the only data a multi-GPU caller has to all-reduce.
+#include "common.cuh"
+
+namespace gsp {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBins = GSP_SELECT_BINS;
+constexpr int kPasses = GSP_SELECT_PASSES;
+constexpr int kMaxBlocks = 1184;  // 148 SMs x 8 resident CTAs
+static_assert(kBins == 2048, "pass layout assumes 11-bit digits");
+
+__host__ __device__ __forceinline__ int pass_shift(int p) { return p < 5 ? 53 - 11 * p : 0; }
+__host__ __device__ __forceinline__ int pass_bits(int p) { return p < 5 ? 11 : 9; }
+
+struct SelectState {
+    uint64_t prefix;      // digits fixed so far, in place
+    int64_t remaining;    // rank still to resolve inside the current prefix bucket (1-based); after the last
+                          // pass: how many members of the tie class are kept
+    int64_t num_keep;
+    int32_t keep_lowest;
+    int32_t empty;        // num_keep == 0: keep nothing
+    int64_t block_ties[kMaxBlocks];
+};
+static_assert(sizeof(SelectState) <= 64 + 8 * kMaxBlocks, "state layout");
+
+// keep_lowest selects the smallest keys; top-k selects the smallest INVERTED keys, so one code path serves both.
+__device__ __forceinline__ uint64_t select_key(double s, int keep_lowest) {
+    uint64_t k = ordered_key(s);
+    return keep_lowest ? k : ~k;
+}
+
+__global__ void begin_kernel(SelectState* st, int64_t num_keep, int keep_lowest) {
+    st->prefix = 0;
+    st->remaining = num_keep;
+    st->num_keep = num_keep;
+    st->keep_lowest = keep_lowest;
+    st->empty = num_keep <= 0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+histogram_kernel(const double* __restrict__ scores, int64_t count, const uint8_t* __restrict__ exclude,
+                 const SelectState* __restrict__ st, int pass, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int sh[kBins];
+    for (int i = threadIdx.x; i < kBins; i += kThreads) sh[i] = 0;
+    __syncthreads();
+    const int shift = pass_shift(pass), bits = pass_bits(pass);
+    const int keep_lowest = st->keep_lowest;
+    const uint64_t prefix = st->prefix;
+    const int hi_shift = shift + bits;  // bits above the current digit must match the prefix
+    const unsigned int digit_mask = (1u << bits) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads; base < count; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        bool live = i < count;
+        unsigned int digit = 0;
+        if (live) {
+            if (exclude && exclude[i]) live = false;
+            else {
+                uint64_t k = select_key(scores[i], keep_lowest);
+                if (hi_shift < 64 && (k >> hi_shift) != (prefix >> hi_shift)) live = false;
+                digit = (unsigned int)(k >> shift) & digit_mask;
+            }
+        }
+        // heavy tie classes (e.g. Jaccard's zeros) put whole warps on one bin: one atomic for the warp
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (live_mask == 0) continue;
+        const int leader = __ffs(live_mask) - 1;
+        const unsigned int lead_digit = __shfl_sync(0xffffffffu, digit, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, live && digit == lead_digit);
+        if (same == live_mask) {
+            if ((threadIdx.x & 31) == leader) atomicAdd(&sh[lead_digit], (unsigned int)__popc(live_mask));
+        } else if (live) {
+            atomicAdd(&sh[digit], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (1 << bits); i += kThreads)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// One warp: find the bucket holding the `remaining`-th smallest live key and descend into it.
+__global__ void pick_kernel(SelectState* st, const unsigned long long* __restrict__ hist, int pass) {
+    if (st->empty) return;
+    const int lane = threadIdx.x;
+    const int bits = pass_bits(pass), shift = pass_shift(pass);
+    const int nbins = 1 << bits, per = nbins / 32;
+    unsigned long long local = 0;
+    for (int i = 0; i < per; ++i) local += hist[lane * per + i];
+    unsigned long long incl = local;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned long long excl = incl - local;
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long want = (unsigned long long)st->remaining;
+    if (want > total) want = total;  // caller asked for more than there is: keep everything
+    if (total == 0) return;
+    const bool mine = want > excl && want <= incl;
+    if (mine) {
+        unsigned long long run = excl;
+        for (int i = 0; i < per; ++i) {
+            unsigned long long h = hist[lane * per + i];
+            if (want <= run + h) {
+                st->prefix |= (uint64_t)(lane * per + i) << shift;
+                st->remaining = (int64_t)(want - run);
+                break;
+            }
+            run += h;
+        }
+    }
+}
+
+__device__ __forceinline__ int64_t chunk_size(int64_t count, int blocks) {
+    int64_t c = (count + blocks - 1) / blocks;
+    return (c + kThreads - 1) / kThreads * kThreads;
+}
+
+__global__ void __launch_bounds__(kThreads)
+count_ties_kernel(const double* __restrict__ scores, int64_t count, const uint8_t* __restrict__ exclude,
+                  SelectState* st, unsigned long long* total) {
+    __shared__ unsigned long long sh;
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    const int keep_lowest = st->keep_lowest;
+    const uint64_t t = st->prefix;
+    const int64_t chunk = chunk_size(count, gridDim.x);
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+    unsigned long long c = 0;
+    if (!st->empty)
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads)
+            c += !(exclude && exclude[i]) && select_key(scores[i], keep_lowest) == t;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->block_ties[blockIdx.x] = (int64_t)sh;
+        if (sh) atomicAdd(total, sh);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+write_mask_kernel(const double* __restrict__ scores, int64_t count, const uint8_t* exclude /* may alias mask */,
+                  const SelectState* __restrict__ st, const int64_t* __restrict__ ties_before_p,
+                  const int64_t* __restrict__ ties_total_p, int or_into, uint8_t* mask) {
+    __shared__ long long warp_sums[kThreads / 32];
+    __shared__ long long block_base;
+    const int keep_lowest = st->keep_lowest;
+    const bool empty = st->empty;
+    const uint64_t t = st->prefix;
+    const int64_t need = st->remaining;
+    const int64_t ties_total = *ties_total_p;
+    // window of global tie ranks (position order) that are kept
+    const int64_t win_lo = keep_lowest ? 0 : ties_total - need;
+    const int64_t win_hi = keep_lowest ? need : ties_total;
+    const bool all_ties = need >= ties_total;   // no rank bookkeeping needed
+    const int64_t chunk = chunk_size(count, gridDim.x);
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+
+    if (!all_ties && !empty) {  // ties in earlier blocks (and on lower ranks)
+        long long s = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += kThreads) s += st->block_ties[b];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = *ties_before_p;
+            for (int w = 0; w < kThreads / 32; ++w) tot += warp_sums[w];
+            block_base = tot;
+        }
+        __syncthreads();
+    }
+    long long running = (!all_ties && !empty) ? block_base : 0;
+    for (int64_t base = lo; base < hi; base += kThreads) {
+        const int64_t i = base + threadIdx.x;
+        const bool in = i < hi;
+        bool excluded = false, below = false, tie = false;
+        if (in && !empty) {
+            excluded = exclude && exclude[i];
+            if (!excluded) {
+                uint64_t k = select_key(scores[i], keep_lowest);
+                below = k < t;
+                tie = k == t;
+            }
+        } else if (in) {
+            excluded = exclude && exclude[i];
+        }
+        bool keep = below;
+        if (all_ties) {
+            keep = keep || tie;
+        } else if (!empty) {
+            // block-wide exclusive rank of this tie in position order
+            const unsigned bal = __ballot_sync(0xffffffffu, tie);
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            __syncthreads();  // warp_sums reuse
+            if (lane == 0) warp_sums[warp] = __popc(bal);
+            __syncthreads();
+            long long before = running;
+            for (int w = 0; w < warp; ++w) before += warp_sums[w];
+            long long tile_total = 0;
+            for (int w = 0; w < kThreads / 32; ++w) tile_total += warp_sums[w];
+            const long long rank = before + __popc(bal & ((1u << lane) - 1u));
+            if (tie && rank >= win_lo && rank < win_hi) keep = true;
+            running += tile_total;
+        }
+        if (in) {
+            if (!or_into) mask[i] = keep ? 1 : 0;
+            else if (keep) mask[i] = 1;  // union with what is already marked (excluded entries are never kept here)
+        }
+    }
+}
+
+// ---- degree-aware guarantee (reference core.py:421-435) -------------------------------------------------
+__global__ void node_best_key_kernel(const int64_t* __restrict__ src, const double* __restrict__ scores, int64_t count,
+                                     const uint8_t* __restrict__ mask, unsigned long long* __restrict__ best) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask[i]) continue;
+        atomicMax(&best[src[i]], (unsigned long long)ordered_key(scores[i]) );
+    }
+}
+
+__global__ void node_best_pos_kernel(const int64_t* __restrict__ src, const double* __restrict__ scores, int64_t count,
+                                     const uint8_t* __restrict__ mask, const unsigned long long* __restrict__ best,
+                                     long long* __restrict__ best_pos) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask[i]) continue;
+        const int64_t v = src[i];
+        if ((unsigned long long)ordered_key(scores[i]) == best[v]) atomicMax(&best_pos[v], (long long)i);
+    }
+}
+
+__global__ void node_mark_kernel(int64_t num_nodes, long long* __restrict__ best_pos, unsigned long long* __restrict__ best,
+                                 uint8_t* __restrict__ mask, unsigned long long* __restrict__ marked) {
+    unsigned long long c = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < num_nodes; v += (int64_t)gridDim.x * blockDim.x) {
+        const long long p = best_pos[v];
+        if (p >= 0) {
+            mask[p] = 1;
+            ++c;
+        }
+        best_pos[v] = -1;  // reset for the next round
+        best[v] = 0;
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(marked, c);
+}
+
+__global__ void fill_i64_kernel(int64_t n, long long* p, long long v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- compaction + "-W" weights ---------------------------------------------------------------------------
+struct CompactScratch {
+    unsigned long long min_key, max_key;
+    long long block_counts[kMaxBlocks];
+};
+
+__device__ __forceinline__ double key_to_double(uint64_t k) {
+    uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(kThreads)
+compact_count_kernel(int64_t count, const uint8_t* __restrict__ mask, const double* __restrict__ scores,
+                     CompactScratch* sc) {
+    __shared__ unsigned long long sh_cnt, sh_min, sh_max;
+    if (threadIdx.x == 0) { sh_cnt = 0; sh_min = ~0ull; sh_max = 0; }
+    __syncthreads();
+    const int64_t chunk = chunk_size(count, gridDim.x);
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+    unsigned long long c = 0, mn = ~0ull, mx = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        if (mask[i]) {
+            ++c;
+            if (scores) {
+                uint64_t k = ordered_key(scores[i]);
+                mn = k < mn ? k : mn;
+                mx = k > mx ? k : mx;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh_cnt, c);
+        atomicMin(&sh_min, mn);
+        atomicMax(&sh_max, mx);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc->block_counts[blockIdx.x] = (long long)sh_cnt;
+        if (scores && sh_cnt) {
+            atomicMin(&sc->min_key, sh_min);
+            atomicMax(&sc->max_key, sh_max);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+compact_scatter_kernel(const int64_t* __restrict__ ei, int64_t ld, int64_t count, const uint8_t* __restrict__ mask,
+                       const double* __restrict__ scores, int invert, const CompactScratch* __restrict__ sc,
+                       int64_t* __restrict__ out_ei, int64_t out_ld, float* __restrict__ out_w,
+                       int64_t* __restrict__ num_kept) {
+    __shared__ long long warp_sums[kThreads / 32];
+    __shared__ long long block_base;
+    {
+        long long s = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += kThreads) s += sc->block_counts[b];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long tot = 0;
+            for (int w = 0; w < kThreads / 32; ++w) tot += warp_sums[w];
+            block_base = tot;
+            if (blockIdx.x == gridDim.x - 1 && num_kept) *num_kept = tot + sc->block_counts[blockIdx.x];
+        }
+        __syncthreads();
+    }
+    double mn = 0.0, denom = 1.0;
+    if (out_w && scores) {
+        mn = key_to_double(sc->min_key);
+        const double mx = key_to_double(sc->max_key);
+        denom = __dadd_rn(__dsub_rn(mx, mn), 1e-8);  // (mx - mn + 1e-8), roman_empire_gpu.py:251
+    }
+    const int64_t chunk = chunk_size(count, gridDim.x);
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+    long long running = block_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = lo; base < hi; base += kThreads) {
+        const int64_t i = base + threadIdx.x;
+        const bool keep = i < hi && mask[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();
+        if (lane == 0) warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        long long before = running, tile_total = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+            if (w < warp) before += warp_sums[w];
+            tile_total += warp_sums[w];
+        }
+        if (keep) {
+            const long long p = before + __popc(bal & ((1u << lane) - 1u));
+            if (p < out_ld) {
+                out_ei[p] = ei[i];
+                out_ei[out_ld + p] = ei[ld + i];
+                if (out_w && scores) {
+                    double w = __ddiv_rn(__dsub_rn(scores[i], mn), denom);
+                    if (invert) w = __dsub_rn(1.0, w);
+                    out_w[p] = (float)w;  // torch.tensor(norm, dtype=float32): round to nearest
+                }
+            }
+        }
+        running += tile_total;
+    }
+}
+
+int blocks_for(int64_t count) {
+    int64_t b = (count + 4 * kThreads - 1) / (4 * kThreads);
+    if (b < 1) b = 1;
+    if (b > kMaxBlocks) b = kMaxBlocks;
+    return (int)b;
+}
+
+}  // namespace
+}  // namespace gsp
+
+using namespace gsp;
+
+static_assert(sizeof(SelectState) <= GSP_SELECT_STATE_BYTES, "GSP_SELECT_STATE_BYTES too small");
+
+GSP_API int gsp_select_begin(void* d_state, int64_t num_keep, int keep_lowest, void* stream) {
+    GSP_REQUIRE(d_state != nullptr, "d_state is NULL");
+    GSP_REQUIRE(num_keep >= 0, "num_keep must be >= 0");
+    begin_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state), num_keep, keep_lowest ? 1 : 0);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_histogram(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                                 int pass, uint64_t* d_hist, void* stream) {
+    GSP_REQUIRE(d_state && d_hist, "NULL argument");
+    GSP_REQUIRE(count >= 0 && (count == 0 || d_scores), "bad scores");
+    GSP_REQUIRE(pass >= 0 && pass < kPasses, "pass out of range");
+    cudaStream_t s = as_stream(stream);
+    GSP_CUDA_TRY(cudaMemsetAsync(d_hist, 0, kBins * sizeof(uint64_t), s));
+    if (count == 0) return GSP_OK;
+    histogram_kernel<<<grid_for(count, 4 * kThreads, 8), kThreads, 0, s>>>(
+        d_scores, count, d_exclude, reinterpret_cast<const SelectState*>(d_state), pass,
+        reinterpret_cast<unsigned long long*>(d_hist));
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_pick(void* d_state, const uint64_t* d_hist, int pass, void* stream) {
+    GSP_REQUIRE(d_state && d_hist, "NULL argument");
+    GSP_REQUIRE(pass >= 0 && pass < kPasses, "pass out of range");
+    pick_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state),
+                                                 reinterpret_cast<const unsigned long long*>(d_hist), pass);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_count_ties(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                                  int64_t* d_tie_count, void* stream) {
+    GSP_REQUIRE(d_state && d_tie_count, "NULL argument");
+    cudaStream_t s = as_stream(stream);
+    GSP_CUDA_TRY(cudaMemsetAsync(d_tie_count, 0, sizeof(int64_t), s));
+    if (count == 0) return GSP_OK;
+    count_ties_kernel<<<blocks_for(count), kThreads, 0, s>>>(
+        d_scores, count, d_exclude, reinterpret_cast<SelectState*>(const_cast<void*>(d_state)),
+        reinterpret_cast<unsigned long long*>(d_tie_count));
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_write_mask(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                                  const int64_t* d_ties_before, const int64_t* d_ties_total, int or_into, uint8_t* d_mask,
+                                  void* stream) {
+    GSP_REQUIRE(d_state && d_ties_before && d_ties_total, "NULL argument");
+    if (count == 0) return GSP_OK;
+    GSP_REQUIRE(d_mask != nullptr, "d_mask is NULL");
+    write_mask_kernel<<<blocks_for(count), kThreads, 0, as_stream(stream)>>>(
+        d_scores, count, d_exclude, reinterpret_cast<const SelectState*>(d_state), d_ties_before, d_ties_total, or_into,
+        d_mask);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_mask(const double* d_scores, int64_t count, int64_t num_keep, int keep_lowest,
+                            const uint8_t* d_exclude, int or_into, uint8_t* d_mask, void* stream) {
+    GSP_REQUIRE(count >= 0 && num_keep >= 0, "negative size");
+    if (count == 0) return GSP_OK;
+    cudaStream_t s = as_stream(stream);
+    Scratch<char> state;
+    Scratch<uint64_t> hist;
+    Scratch<int64_t> ties;  // [0] = total ties, [1] = 0 (ties before this shard)
+    GSP_CUDA_TRY(state.alloc(GSP_SELECT_STATE_BYTES, s));
+    GSP_CUDA_TRY(hist.alloc(kBins, s));
+    GSP_CUDA_TRY(ties.alloc(2, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(ties.ptr, 0, 2 * sizeof(int64_t), s));
+    if (int rc = gsp_select_begin(state.ptr, num_keep, keep_lowest, stream)) return rc;
+    for (int p = 0; p < kPasses; ++p) {
+        if (int rc = gsp_select_histogram(d_scores, count, d_exclude, state.ptr, p, hist.ptr, stream)) return rc;
+        if (int rc = gsp_select_pick(state.ptr, hist.ptr, p, stream)) return rc;
+    }
+    if (int rc = gsp_select_count_ties(d_scores, count, d_exclude, state.ptr, ties.ptr, stream)) return rc;
+    return gsp_select_write_mask(d_scores, count, d_exclude, state.ptr, ties.ptr + 1, ties.ptr, or_into, d_mask, stream);
+}
+
+GSP_API int gsp_degree_aware_guarantee(const int64_t* d_src, const double* d_scores, int64_t count, int64_t num_nodes,
+                                       int32_t min_per_node, uint8_t* d_mask, int64_t* d_num_marked, void* stream) {
+    GSP_REQUIRE(count >= 0 && num_nodes >= 0 && min_per_node >= 0, "negative size");
+    GSP_REQUIRE(d_num_marked != nullptr, "d_num_marked is NULL");
+    cudaStream_t s = as_stream(stream);
+    GSP_CUDA_TRY(cudaMemsetAsync(d_num_marked, 0, sizeof(int64_t), s));
+    if (count == 0) return GSP_OK;
+    GSP_REQUIRE(d_src && d_scores && d_mask, "NULL argument");
+    GSP_CUDA_TRY(cudaMemsetAsync(d_mask, 0, (size_t)count, s));
+    if (num_nodes == 0 || min_per_node == 0) return GSP_OK;
+    Scratch<unsigned long long> best;
+    Scratch<long long> best_pos;
+    GSP_CUDA_TRY(best.alloc(num_nodes, s));
+    GSP_CUDA_TRY(best_pos.alloc(num_nodes, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(best.ptr, 0, (size_t)num_nodes * sizeof(unsigned long long), s));
+    fill_i64_kernel<<<grid_for(num_nodes, 256), 256, 0, s>>>(num_nodes, best_pos.ptr, -1);
+    GSP_CHECK_LAUNCH();
+    const int grid = grid_for(count, 256);
+    for (int round = 0; round < min_per_node; ++round) {
+        node_best_key_kernel<<<grid, 256, 0, s>>>(d_src, d_scores, count, d_mask, best.ptr);
+        GSP_CHECK_LAUNCH();
+        node_best_pos_kernel<<<grid, 256, 0, s>>>(d_src, d_scores, count, d_mask, best.ptr, best_pos.ptr);
+        GSP_CHECK_LAUNCH();
+        node_mark_kernel<<<grid_for(num_nodes, 256), 256, 0, s>>>(num_nodes, best_pos.ptr, best.ptr, d_mask,
+                                                                  reinterpret_cast<unsigned long long*>(d_num_marked));
+        GSP_CHECK_LAUNCH();
+    }
+    return GSP_OK;
+}
+
+GSP_API int gsp_compact_edges(const int64_t* d_edge_index, int64_t ld, int64_t count, const uint8_t* d_mask,
+                              const double* d_scores, int invert_weights, int64_t* d_out_edge_index, int64_t out_ld,
+                              float* d_out_weight, int64_t* d_num_kept, void* stream) {
+    GSP_REQUIRE(count >= 0 && ld >= count && out_ld >= 0, "bad sizes");
+    cudaStream_t s = as_stream(stream);
+    if (count == 0) {
+        if (d_num_kept) GSP_CUDA_TRY(cudaMemsetAsync(d_num_kept, 0, sizeof(int64_t), s));
+        return GSP_OK;
+    }
+    GSP_REQUIRE(d_edge_index && d_mask, "NULL argument");
+    GSP_REQUIRE(out_ld == 0 || d_out_edge_index, "d_out_edge_index is NULL");
+    Scratch<CompactScratch> sc;
+    GSP_CUDA_TRY(sc.alloc(1, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(sc.ptr, 0, sizeof(CompactScratch), s));
+    GSP_CUDA_TRY(cudaMemsetAsync(&sc.ptr->min_key, 0xff, sizeof(unsigned long long), s));
+    const int blocks = blocks_for(count);
+    const double* sc_scores = d_out_weight ? d_scores : nullptr;
+    compact_count_kernel<<<blocks, kThreads, 0, s>>>(count, d_mask, sc_scores, sc.ptr);
+    GSP_CHECK_LAUNCH();
+    compact_scatter_kernel<<<blocks, kThreads, 0, s>>>(d_edge_index, ld, count, d_mask, sc_scores, invert_weights, sc.ptr,
+                                                       d_out_edge_index, out_ld, d_out_weight, d_num_kept);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}

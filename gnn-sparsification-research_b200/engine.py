@@ -1,0 +1,244 @@
+"""Device-tensor layer over the C ABI: torch owns the memory and the streams, libgsp.so does the work.
+
+Everything here takes and returns CUDA tensors on the graph's device and enqueues on torch's current
+stream; nothing synchronises except graph construction (one host read of the merged nnz) and the
+explicit `.item()` calls documented below.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+class DeviceGraph:
+    """Canonical CSR of a directed edge list, resident on one GPU (reference core.py:70-74)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, values: Optional[torch.Tensor] = None):
+        _lib.require_cuda()
+        if not edge_index.is_cuda:
+            raise _lib.GspError("DeviceGraph needs a CUDA edge_index")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
+        self.device = edge_index.device
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+        e = ei.size(1)
+        val = None
+        if values is not None:
+            val = values.to(device=self.device, dtype=torch.float64).contiguous()
+        with torch.cuda.device(self.device):
+            row_ptr = C.c_void_p(ei.data_ptr()) if e else None
+            col_ptr = C.c_void_p(ei.data_ptr() + 8 * e) if e else None
+            check(self._lib.gsp_graph_create(int(num_nodes), e, row_ptr, col_ptr, ptr(val), stream_ptr(self.device),
+                                             C.byref(self._handle)))
+        info = _lib.GraphInfo()
+        check(self._lib.gsp_graph_get_info(self._handle, C.byref(info)))
+        self.num_nodes = info.num_nodes
+        self.num_input_edges = info.num_input_edges
+        self.nnz = info.nnz
+        self.num_undirected = info.num_undirected
+        self.max_degree = info.max_degree
+        self.sum_degree_sq = info.sum_degree_sq
+        self.symmetric = bool(info.symmetric)
+        self.input_canonical = bool(info.input_canonical)
+        self.unit_weights = bool(info.unit_weights)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.gsp_graph_destroy(h)
+            except Exception:
+                pass
+            self._handle = C.c_void_p()
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return stream_ptr(self.device)
+
+    def _range(self, e_begin, e_end) -> Tuple[int, int]:
+        e_begin = 0 if e_begin is None else int(e_begin)
+        e_end = self.nnz if e_end is None else int(e_end)
+        if not 0 <= e_begin <= e_end <= self.nnz:
+            raise ValueError(f"edge range [{e_begin}, {e_end}) outside [0, {self.nnz}]")
+        return e_begin, e_end
+
+    def _empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    # -- CSR export ------------------------------------------------------------------------------
+    def export(self, with_data=True, with_rows=False):
+        indptr = self._empty(self.num_nodes + 1, torch.int64)
+        indices = self._empty(self.nnz, torch.int32)
+        data = self._empty(self.nnz, torch.float64) if with_data else None
+        rows = self._empty(self.nnz, torch.int32) if with_rows else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_graph_export(self._handle, ptr(indptr), ptr(indices), ptr(data), ptr(rows), self._stream()))
+        return indptr, indices, data, rows
+
+    def degrees(self) -> torch.Tensor:
+        deg = self._empty(self.num_nodes, torch.int32)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_graph_degrees(self._handle, ptr(deg), self._stream()))
+        return deg
+
+    def undirected_ids(self) -> torch.Tensor:
+        uid = self._empty(self.nnz, torch.int32)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_graph_undirected_ids(self._handle, ptr(uid), self._stream()))
+        return uid
+
+    # -- scoring ---------------------------------------------------------------------------------
+    def jaccard(self, e_begin=None, e_end=None, return_counts=False, out=None):
+        b, e = self._range(e_begin, e_end)
+        score = self._empty(e - b, torch.float64) if out is None else out
+        inter = self._empty(e - b, torch.int32) if return_counts else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_jaccard(self._handle, b, e, ptr(inter), ptr(score), self._stream()))
+        return (score, inter) if return_counts else score
+
+    def aa_node_weights(self) -> torch.Tensor:
+        w = self._empty(self.num_nodes, torch.float64)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_aa_node_weights(self._handle, ptr(w), self._stream()))
+        return w
+
+    def adamic_adar(self, node_weights: Optional[torch.Tensor] = None, e_begin=None, e_end=None, out=None):
+        b, e = self._range(e_begin, e_end)
+        if node_weights is not None:
+            node_weights = node_weights.to(device=self.device, dtype=torch.float64).contiguous()
+            if node_weights.numel() != self.num_nodes:
+                raise ValueError("node_weights must have num_nodes entries")
+        score = self._empty(e - b, torch.float64) if out is None else out
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_adamic_adar(self._handle, ptr(node_weights), b, e, ptr(score), self._stream()))
+        return score
+
+    def degree_product(self, e_begin=None, e_end=None, out=None):
+        b, e = self._range(e_begin, e_end)
+        score = self._empty(e - b, torch.float64) if out is None else out
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_degree_product(self._handle, b, e, ptr(score), self._stream()))
+        return score
+
+    def normalize_features(self, x: torch.Tensor) -> torch.Tensor:
+        """Row-normalised features in the dtype of `x` (fp32 or fp64), reference metrics.py:344-346."""
+        if x.dim() != 2 or x.size(0) != self.num_nodes:
+            raise ValueError("features must have shape [num_nodes, d]")
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float64)  # NumPy promotes integer features to float64 in linalg.norm / divide
+        x = x.to(self.device).contiguous()
+        xhat = torch.empty_like(x)
+        fn = self._lib.gsp_featcos_normalize_f32 if x.dtype == torch.float32 else self._lib.gsp_featcos_normalize_f64
+        with torch.cuda.device(self.device):
+            check(fn(x.size(0), x.size(1), ptr(x), x.size(1), ptr(xhat), x.size(1), self._stream()))
+        return xhat
+
+    def feature_cosine(self, xhat: torch.Tensor, e_begin=None, e_end=None, out=None):
+        b, e = self._range(e_begin, e_end)
+        score = self._empty(e - b, torch.float64) if out is None else out
+        fn = self._lib.gsp_featcos_f32 if xhat.dtype == torch.float32 else self._lib.gsp_featcos_f64
+        with torch.cuda.device(self.device):
+            check(fn(self._handle, ptr(xhat), xhat.size(1), xhat.stride(0), b, e, ptr(score), self._stream()))
+        return score
+
+    def approx_er_partial(self, projection: torch.Tensor, max_iters=500, rtol=1e-6, reg=1e-6, e_begin=None, e_end=None,
+                          return_iters=False):
+        """Partial resistance sums over the columns of `projection` (fp64 [m, k], any row stride)."""
+        b, e = self._range(e_begin, e_end)
+        if projection.dim() != 2 or projection.size(0) != self.num_undirected or projection.dtype != torch.float64:
+            raise ValueError("projection must be fp64 [num_undirected, k]")
+        if projection.stride(1) != 1:
+            projection = projection.contiguous()
+        k = projection.size(1)
+        out = self._empty(e - b, torch.float64)
+        iters = self._empty(k, torch.int32) if return_iters else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_approx_er_partial(self._handle, ptr(projection), projection.stride(0), k, int(max_iters),
+                                                  float(rtol), float(reg), b, e, ptr(out), ptr(iters), self._stream()))
+        return (out, iters) if return_iters else out
+
+    def er_finalize(self, partial: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_er_finalize(ptr(partial), partial.numel(), self._stream()))
+        return partial
+
+
+# ---- selection / compaction on raw tensors -----------------------------------------------------------
+def select_mask(scores: torch.Tensor, num_keep: int, keep_lowest: bool = False, exclude: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, or_into: bool = False) -> torch.Tensor:
+    """uint8 keep-mask of the `num_keep` highest (lowest) scores, ties broken by position (stable-argsort contract)."""
+    lib = _lib.load()
+    n = scores.numel()
+    mask = torch.empty(n, dtype=torch.uint8, device=scores.device) if out is None else out
+    with torch.cuda.device(scores.device):
+        check(lib.gsp_select_mask(ptr(scores), n, int(num_keep), int(bool(keep_lowest)), ptr(exclude), int(bool(or_into)),
+                                  ptr(mask), stream_ptr(scores.device)))
+    return mask
+
+
+def select_mask_sharded(scores: torch.Tensor, num_keep: int, keep_lowest: bool, group, exclude=None, out=None,
+                        or_into: bool = False) -> torch.Tensor:
+    """Distributed radix select: `scores` is this rank's contiguous slice (rank order == position order).
+
+    Only the 16 KB histograms (all-reduce) and one tie count per rank (all-gather) cross NVLink."""
+    import torch.distributed as dist
+
+    lib = _lib.load()
+    dev = scores.device
+    n = scores.numel()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev) if out is None else out
+    state = torch.empty(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=dev)
+    hist = torch.empty(_lib.SELECT_BINS, dtype=torch.int64, device=dev)
+    ties = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        s = stream_ptr(dev)
+        check(lib.gsp_select_begin(ptr(state), int(num_keep), int(bool(keep_lowest)), s))
+        for p in range(_lib.SELECT_PASSES):
+            check(lib.gsp_select_histogram(ptr(scores), n, ptr(exclude), ptr(state), p, ptr(hist), s))
+            dist.all_reduce(hist, group=group)
+            check(lib.gsp_select_pick(ptr(state), ptr(hist), p, s))
+        check(lib.gsp_select_count_ties(ptr(scores), n, ptr(exclude), ptr(state), ptr(ties), s))
+        all_ties = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_ties, ties, group=group)
+        before = all_ties[:rank].sum().reshape(1)
+        total = all_ties.sum().reshape(1)
+        check(lib.gsp_select_write_mask(ptr(scores), n, ptr(exclude), ptr(state), ptr(before), ptr(total),
+                                        int(bool(or_into)), ptr(mask), s))
+    return mask
+
+
+def degree_aware_guarantee(src: torch.Tensor, scores: torch.Tensor, num_nodes: int, min_per_node: int):
+    """(uint8 mask of guaranteed edges, int64[1] count) — reference core.py:421-435."""
+    lib = _lib.load()
+    n = src.numel()
+    mask = torch.empty(n, dtype=torch.uint8, device=src.device)
+    marked = torch.empty(1, dtype=torch.int64, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.gsp_degree_aware_guarantee(ptr(src), ptr(scores), n, int(num_nodes), int(min_per_node), ptr(mask),
+                                             ptr(marked), stream_ptr(src.device)))
+    return mask, marked
+
+
+def compact_edges(edge_index: torch.Tensor, mask: torch.Tensor, num_kept: int, scores: Optional[torch.Tensor] = None,
+                  with_weights: bool = False, invert_weights: bool = False):
+    """`edge_index[:, mask]` (+ optional min-max "-W" weights) without leaving the device."""
+    lib = _lib.load()
+    dev = edge_index.device
+    e = edge_index.size(1)
+    ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+    out = torch.empty((2, int(num_kept)), dtype=torch.int64, device=dev)
+    w = torch.empty(int(num_kept), dtype=torch.float32, device=dev) if with_weights else None
+    count = torch.empty(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gsp_compact_edges(ptr(ei), e, e, ptr(mask), ptr(scores) if with_weights else None,
+                                    int(bool(invert_weights)), ptr(out), int(num_kept), ptr(w), ptr(count),
+                                    stream_ptr(dev)))
+    return out, w, count

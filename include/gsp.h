@@ -1,0 +1,184 @@
+/*
+ * gsp.h — C ABI of libgsp.so, the B200 (sm_100a) edge-scoring sparsification engine.
+ *
+ * The reference (ilias-laoukili/gnn-sparsification-research) is pure Python: its "plugin
+ * boundary" for this path is the class `GraphSparsifier` plus five `calculate_*_scores`
+ * functions (reference src/sparsification/__init__.py:16-28), not an FFI. This header is the
+ * C boundary a maintainer would bind from that Python layer (ctypes stub in INTEGRATION.md);
+ * each entry point cites the reference statement(s) it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/torch types cross the boundary.
+ *   - Every `d_*` pointer is DEVICE memory owned by the caller, on the graph's device. Outputs
+ *     are caller-allocated. The library owns only `gsp_graph` and stream-ordered scratch.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream). All work
+ *     is enqueued on it; calls return without synchronising unless stated otherwise.
+ *   - Return value: 0 on success, non-zero `gsp_status` otherwise; `gsp_last_error()` returns
+ *     a thread-local message. No exceptions cross the ABI. There is NO CPU fallback: without
+ *     a CUDA device every compute entry point fails with GSP_ERR_CUDA.
+ *   - Edge order everywhere is canonical CSR order (rows ascending, columns ascending inside a
+ *     row, duplicates merged) == the order of SciPy's `adj.nonzero()` that every reference
+ *     score vector uses. Scoring calls take a half-open range
+ *     [e_begin, e_end) of canonical edge positions and write `e_end - e_begin` values, so a
+ *     caller can shard edges over GPUs with the CSR replicated.
+ */
+#ifndef GSP_H_
+#define GSP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSP_VERSION 100 /* major*100 + minor */
+
+typedef enum gsp_status {
+    GSP_OK = 0,
+    GSP_ERR_INVALID = 1, /* bad argument (null pointer, negative size, index out of range, ...) */
+    GSP_ERR_CUDA = 2,    /* a CUDA runtime call failed / no device */
+    GSP_ERR_NOMEM = 3,
+    GSP_ERR_UNSUPPORTED = 4
+} gsp_status;
+
+typedef struct gsp_graph gsp_graph; /* opaque: canonical CSR (+ transpose when asymmetric) on one device */
+
+typedef struct gsp_graph_info {
+    int64_t num_nodes;
+    int64_t num_input_edges; /* columns of the edge_index handed in (reference `num_edges`, core.py:67) */
+    int64_t nnz;             /* canonical entries == length of every score vector (adj.nnz) */
+    int64_t num_undirected;  /* entries with row < col (ApproxER's m, metrics.py:239-242) */
+    int64_t max_degree;
+    double sum_degree_sq;    /* sum_u deg(u)^2: intersection work / roofline bytes */
+    int32_t symmetric;       /* pattern symmetric => row(v) stands in for col(v) in Jaccard */
+    int32_t input_canonical; /* input was already (row,col)-sorted and duplicate free */
+    int32_t unit_weights;    /* every merged value == 1.0 */
+    int32_t device;
+} gsp_graph_info;
+
+int gsp_version(void);
+const char* gsp_last_error(void);
+
+/* ---- graph ----------------------------------------------------------------------------------
+ * Replaces reference core.py:70-74: sp.csr_matrix((ones(E), (row, col)), shape=(n, n)).
+ * d_row/d_col: int64[num_edges] (the two rows of PyG's edge_index). d_val: optional fp64
+ * values (NULL = ones); duplicates are summed (data = multiplicity), explicit zeros dropped
+ * like `adj.nonzero()`. Synchronises `stream` once (the merged nnz is needed on the host).
+ * Fails with GSP_ERR_INVALID if an index is outside [0, num_nodes). */
+int gsp_graph_create(int64_t num_nodes, int64_t num_edges, const int64_t* d_row, const int64_t* d_col,
+                     const double* d_val, void* stream, gsp_graph** out);
+void gsp_graph_destroy(gsp_graph* g);
+int gsp_graph_get_info(const gsp_graph* g, gsp_graph_info* out);
+/* Copies the canonical CSR out (any pointer may be NULL): indptr int64[n+1], indices int32[nnz],
+ * data fp64[nnz], rows int32[nnz] (row id of every canonical position, i.e. adj.nonzero()[0]). */
+int gsp_graph_export(const gsp_graph* g, int64_t* d_indptr, int32_t* d_indices, double* d_data, int32_t* d_rows,
+                     void* stream);
+/* int32[n] binarised row degrees (reference metrics.py:44,100). */
+int gsp_graph_degrees(const gsp_graph* g, int32_t* d_deg, void* stream);
+/* int32[nnz]: id of the undirected edge {u,v} each canonical position belongs to (rank of its
+ * (min,max) orientation among row<col positions; -1 for self loops / unmatched directions). */
+int gsp_graph_undirected_ids(const gsp_graph* g, int32_t* d_uid, void* stream);
+
+/* ---- scoring --------------------------------------------------------------------------------
+ * Jaccard — replaces calculate_jaccard_scores, reference metrics.py:43-64:
+ *   I = |row(u) ∩ col(v)| (== (Ab@Ab)[u,v]), score = I / (deg u + deg v - I), 0 when the union is 0.
+ * d_inter (optional) receives the exact integer intersection counts. */
+int gsp_jaccard(const gsp_graph* g, int64_t e_begin, int64_t e_end, int32_t* d_inter, double* d_score, void* stream);
+
+/* Adamic-Adar — replaces calculate_adamic_adar_scores, reference metrics.py:99-121:
+ *   score = sum over x in row(u) ∩ row(v), DESCENDING x, of fl(w[x]*w[x]) (sequential fp64 adds: the
+ *   association order SciPy's SpGEMM uses, needed for bit-equal scores / keep-masks).
+ * d_node_w: fp64[n] node weights 1/sqrt(max(log(deg+1),1e-10)); NULL = computed on device by
+ * gsp_aa_node_weights (CUDA libm; may differ from NumPy's SIMD log in the last bit). */
+int gsp_adamic_adar(const gsp_graph* g, const double* d_node_w, int64_t e_begin, int64_t e_end, double* d_score,
+                    void* stream);
+int gsp_aa_node_weights(const gsp_graph* g, double* d_node_w, void* stream);
+
+/* degree product — replaces reference core.py:167-172 (`degree` metric; raw-value row sums). */
+int gsp_degree_product(const gsp_graph* g, int64_t e_begin, int64_t e_end, double* d_score, void* stream);
+
+/* Feature cosine — replaces calculate_feature_cosine_scores, reference metrics.py:344-358.
+ * Step 1 (per node): xhat = x / max(sqrt(pairwise_sum(x*x)), 1e-10)   [metrics.py:344-346]
+ * Step 2 (per edge): score = (double) max(pairwise_sum(xhat_u * xhat_v), 0)   [metrics.py:351-358]
+ * Arithmetic runs in the feature dtype with NumPy's pairwise-summation tree,
+ * products rounded before they are summed, no FMA contraction. `ld` = row stride in elements. */
+int gsp_featcos_normalize_f32(int64_t num_nodes, int32_t dim, const float* d_x, int64_t ld, float* d_xhat,
+                              int64_t ld_out, void* stream);
+int gsp_featcos_f32(const gsp_graph* g, const float* d_xhat, int32_t dim, int64_t ld, int64_t e_begin, int64_t e_end,
+                    double* d_score, void* stream);
+int gsp_featcos_normalize_f64(int64_t num_nodes, int32_t dim, const double* d_x, int64_t ld, double* d_xhat,
+                              int64_t ld_out, void* stream);
+int gsp_featcos_f64(const gsp_graph* g, const double* d_xhat, int32_t dim, int64_t ld, int64_t e_begin,
+                    int64_t e_end, double* d_score, void* stream);
+
+/* ---- approximate effective resistance ----------------------------------------------------------
+ * Replaces calculate_approx_effective_resistance_scores, reference metrics.py:232-298, for the
+ * projection columns [0, k) of d_R (fp64 [m, ldr] row-major, m = num_undirected; the caller
+ * slices columns to shard them over GPUs):  Y = B R;  Z = CG(L + reg*I, Y) column by column with
+ * SciPy's cg semantics (x0 = 0, test ||r|| < rtol*||b|| before each update, at most max_iters
+ * updates, the partial iterate is kept);  d_partial[e] = sum_j (Z[u,j] - Z[v,j])^2 for e in
+ * [e_begin, e_end). The caller all-reduces partial sums over column shards and then applies
+ * gsp_er_finalize (max(., 1e-10), metrics.py:296-297). d_iters (optional) int32[k] = CG updates per column. */
+int gsp_approx_er_partial(const gsp_graph* g, const double* d_R, int64_t ldr, int32_t k, int32_t max_iters,
+                          double rtol, double reg, int64_t e_begin, int64_t e_end, double* d_partial,
+                          int32_t* d_iters, void* stream);
+int gsp_er_finalize(double* d_score, int64_t count, void* stream);
+
+/* ---- selection ---------------------------------------------------------------------------------
+ * Radix-histogram select with stable (score, position) tie-breaking — replaces the full argsort of
+ * reference core.py:232-240 (and :446-451 with an exclusion mask). Keys are fp64 scores mapped to
+ * order-preserving uint64. Phased so a multi-GPU caller can all-reduce the histograms:
+ *
+ *   gsp_select_begin(state, num_keep, keep_lowest)
+ *   for pass in 0 .. GSP_SELECT_PASSES-1:
+ *       gsp_select_histogram(scores, count, exclude, state, pass, hist)      (local slice)
+ *       [all-reduce hist: uint64[GSP_SELECT_BINS], sum]
+ *       gsp_select_pick(state, hist, pass)
+ *   gsp_select_count_ties(scores, count, exclude, state, tie_count)           (local slice)
+ *   [all-gather tie counts -> ties_before = sum over lower ranks, ties_total]
+ *   gsp_select_write_mask(scores, count, exclude, state, ties_before, ties_total, mask)
+ *
+ * Contract (the reference run with a stable argsort): top-k keeps {s > t} plus the
+ * HIGHEST-position members of {s == t}; keep_lowest keeps {s < t} plus the LOWEST-position members.
+ * `state` is GSP_SELECT_STATE_BYTES of caller-owned device memory. Everything is stream-ordered; no
+ * host synchronisation. gsp_select_mask runs the whole sequence for one GPU.
+ * num_keep must be in [0, number of non-excluded scores]. */
+#define GSP_SELECT_BINS 2048
+#define GSP_SELECT_PASSES 6
+#define GSP_SELECT_STATE_BYTES 16384
+
+int gsp_select_begin(void* d_state, int64_t num_keep, int keep_lowest, void* stream);
+int gsp_select_histogram(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                         int pass, uint64_t* d_hist, void* stream);
+int gsp_select_pick(void* d_state, const uint64_t* d_hist, int pass, void* stream);
+int gsp_select_count_ties(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                          int64_t* d_tie_count, void* stream);
+int gsp_select_write_mask(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
+                          const int64_t* d_ties_before, const int64_t* d_ties_total, int or_into, uint8_t* d_mask,
+                          void* stream);
+int gsp_select_mask(const double* d_scores, int64_t count, int64_t num_keep, int keep_lowest,
+                    const uint8_t* d_exclude, int or_into, uint8_t* d_mask, void* stream);
+
+/* Degree-aware guarantee phase — replaces reference core.py:421-435: for every source node
+ * (d_src = edge_index[0], positional, any order) mark its top min(min_per_node, out-degree) edges by
+ * (score, position). d_mask (uint8[count]) is overwritten; d_num_marked (int64[1]) = |G|. The fill phase
+ * (core.py:444-451) is gsp_select_mask with d_exclude = d_mask, or_into = 1. */
+int gsp_degree_aware_guarantee(const int64_t* d_src, const double* d_scores, int64_t count, int64_t num_nodes,
+                               int32_t min_per_node, uint8_t* d_mask, int64_t* d_num_marked, void* stream);
+
+/* ---- compaction / edge weights -------------------------------------------------------------------
+ * Replaces `edge_index[:, mask]` (reference core.py:242) and the "-W" weight derivation
+ * (scripts/nb05_roman_empire/roman_empire_gpu.py:248-256): w = (s - min)/(max - min + 1e-8) over the kept
+ * scores (1 - w when invert), evaluated in fp64 and rounded to fp32. d_edge_index is int64 [2, count]
+ * (row stride `ld`); outputs keep the original column order. d_out_weight / d_scores may be NULL.
+ * d_num_kept (int64[1]) receives the number of kept columns; out buffers must hold `out_ld` columns. */
+int gsp_compact_edges(const int64_t* d_edge_index, int64_t ld, int64_t count, const uint8_t* d_mask,
+                      const double* d_scores, int invert_weights, int64_t* d_out_edge_index, int64_t out_ld,
+                      float* d_out_weight, int64_t* d_num_kept, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSP_H_ */

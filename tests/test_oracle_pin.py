@@ -1,0 +1,155 @@
+"""Pins the oracles (plain-C restatement + SciPy port) before anything trusts them.
+
+* against the committed golden fixtures (outputs of the live reference, made by
+  oracle/make_golden.py) — runs everywhere, including the GPU box;
+* against the live reference imported from /root/reference — build container only.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import ref_loader
+from oracle import scipy_port as port
+from tests.helpers import RETENTIONS, bits_equal, golden_names, load_golden
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_matches_golden(name):
+    g = load_golden(name)
+    ei, n = g["edge_index"], int(g["num_nodes"])
+    e = ei.shape[1]
+    csr = co.csr_from_edge_index(ei, n)
+    assert csr.nnz == int(g["nnz"])
+    assert np.array_equal(csr.indptr, g["csr_indptr"]) and np.array_equal(csr.indices, g["csr_indices"])
+    assert bits_equal(csr.data, g["csr_data"])
+    scores = {
+        "jaccard": co.calculate_jaccard_scores(csr),
+        "adamic_adar": co.calculate_adamic_adar_scores(csr, node_weights=g["aa_node_w"]),
+        "degree": co.degree_product_scores(csr),
+    }
+    if "x" in g:
+        scores["feature_cosine"] = co.calculate_feature_cosine_scores(csr, g["x"])
+    for m, s in scores.items():
+        assert bits_equal(s, g[f"score_{m}"]), m            # integer/fp64/fp32-tree work: bit-exact
+    if "score_approx_er" in g:
+        er = co.calculate_approx_effective_resistance_scores(csr, epsilon=float(g["er_epsilon"]))
+        np.testing.assert_allclose(er, g["score_approx_er"], rtol=1e-4)      # north_star tolerance
+        scores["approx_er"] = g["score_approx_er"]
+    for m, s in scores.items():
+        if m == "degree":
+            continue
+        for r in RETENTIONS:
+            tag = f"{m}_{int(r * 100)}"
+            for kl in (False, True):
+                assert np.array_equal(co.threshold_mask(s, e, r, kl), g[f"mask_{'low' if kl else 'top'}_{tag}"]), tag
+            if f"mask_dega_{tag}" in g:
+                assert np.array_equal(co.degree_aware_mask(s, ei[0], n, e, r, 1), g[f"mask_dega_{tag}"])
+                assert np.array_equal(co.degree_aware_mask(s, ei[0], n, e, r, 2), g[f"mask_dega2_{tag}"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_scipy_port_matches_golden(name):
+    g = load_golden(name)
+    ei, n = g["edge_index"], int(g["num_nodes"])
+    e = ei.shape[1]
+    adj = port.build_adjacency(ei, n)
+    # Jaccard is integer counts + one IEEE divide: identical on any host. AA goes through
+    # libm log (SIMD-dispatch dependent), so it is pinned with the fixture's own weights in
+    # the C-oracle test and to 1e-12 here.
+    assert bits_equal(port.jaccard(adj), g["score_jaccard"])
+    np.testing.assert_allclose(port.adamic_adar(adj), g["score_adamic_adar"], rtol=1e-12)
+    assert bits_equal(port.degree_product(adj), g["score_degree"])
+    if "x" in g:
+        assert bits_equal(port.feature_cosine(adj, g["x"]), g["score_feature_cosine"])
+    if "score_approx_er" in g:
+        er = port.approx_effective_resistance(adj, epsilon=float(g["er_epsilon"]))
+        np.testing.assert_allclose(er, g["score_approx_er"], rtol=1e-6)
+    s = g["score_jaccard"]
+    for r in RETENTIONS:
+        tag = f"jaccard_{int(r * 100)}"
+        assert np.array_equal(port.threshold_mask(s, e, r), g[f"mask_top_{tag}"])
+        assert np.array_equal(port.threshold_mask(s, e, r, keep_lowest=True), g[f"mask_low_{tag}"])
+        if f"mask_dega_{tag}" in g:
+            assert np.array_equal(port.degree_aware_mask(s, ei[0], n, e, r, 1), g[f"mask_dega_{tag}"])
+            assert np.array_equal(port.degree_aware_mask(s, ei[0], n, e, r, 2), g[f"mask_dega2_{tag}"])
+            assert np.array_equal(port.sampled_mask(s, e, r, 42), g[f"mask_samp_{tag}"])
+            mask = g[f"mask_top_{tag}"]
+            assert bits_equal(port.minmax_edge_weight(s, mask), g[f"weight_top_{tag}"])
+    us, inv = port.precompute_random_scores(ei, n, 42)
+    assert bits_equal(us, g["random_undirected_scores"]) and np.array_equal(inv, g["random_inverse_idx"])
+    for r in RETENTIONS:
+        assert np.array_equal(ei[:, port.random_mask(us, inv, r)], g[f"random_edge_index_{int(r * 100)}"])
+
+
+def test_pairwise_sum_tree_matches_numpy():
+    """the restated tree must equal np.sum / np.add.reduce bit-for-bit."""
+    rng = np.random.default_rng(0)
+    for d in list(range(1, 40)) + [64, 100, 127, 128, 129, 200, 255, 256, 257, 300, 512, 1000, 1433]:
+        a32 = rng.standard_normal(d, dtype=np.float32)
+        assert co.pairwise_sum(a32).tobytes() == np.add.reduce(a32).tobytes(), d
+        a64 = rng.standard_normal(d)
+        assert co.pairwise_sum(a64).tobytes() == np.add.reduce(a64).tobytes(), d
+
+
+def test_scores_to_cost_kat():
+    """The one known-answer test the reference holds for this path (tests/test_sparsification.py:143-150)."""
+    from gsr_b200.core import GraphSparsifier  # host logic only: no device call
+    costs = GraphSparsifier._scores_to_cost(None, np.array([0.5, 1.0, 0.25]), "jaccard")
+    np.testing.assert_allclose(costs, [1.0, 0.0, 3.0])
+
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(800, 6400, 10, 41), (2708, 10556, 12, 1)])
+def test_oracles_match_live_reference(shape):
+    import torch
+    from gsr_b200.data import Data
+    from gsr_b200.synthetic import features, rmat_graph
+
+    n, e, scale, seed = shape
+    ref = ref_loader.load(stable=True)
+    ei = rmat_graph(n, e, scale, seed)
+    x = features(n, 65, seed)
+    sp = ref.GraphSparsifier(Data(edge_index=torch.from_numpy(ei), x=torch.from_numpy(x), num_nodes=n), "cpu")
+    csr = co.csr_from_edge_index(ei, n)
+    adj = port.build_adjacency(ei, n)
+    for m, fn, pfn in (("jaccard", co.calculate_jaccard_scores, port.jaccard),
+                       ("adamic_adar", co.calculate_adamic_adar_scores, port.adamic_adar),
+                       ("degree", co.degree_product_scores, port.degree_product)):
+        want = sp.compute_scores(m)
+        assert bits_equal(fn(csr), want), m
+        assert bits_equal(pfn(adj), want), m
+    want = sp.compute_scores("feature_cosine")
+    assert bits_equal(co.calculate_feature_cosine_scores(csr, x), want)
+    assert bits_equal(port.feature_cosine(adj, x), want)
+    s = sp.compute_scores("jaccard")
+    for r in (0.8, 0.5, 0.13):
+        for kl in (False, True):
+            _, mask = sp.sparsify("jaccard", r, return_mask=True, keep_lowest=kl)
+            assert np.array_equal(co.threshold_mask(s, e, r, kl), mask.numpy())
+    if n <= 1000:
+        _, mask = sp.sparsify_degree_aware("jaccard", 0.5, return_mask=True)
+        assert np.array_equal(co.degree_aware_mask(s, ei[0], n, e, 0.5, 1), mask.numpy())
+        metrics = sys.modules[ref.__name__ + ".metrics"]
+        want = metrics.calculate_approx_effective_resistance_scores(sp.adj, epsilon=1.5)
+        np.testing.assert_allclose(co.calculate_approx_effective_resistance_scores(csr, epsilon=1.5), want, rtol=1e-4)
+        assert bits_equal(port.approx_effective_resistance(adj, epsilon=1.5), want)
+
+
+@needs_ref
+def test_reference_property_tests_hold_for_oracle():
+    """The reference's own property tests (tests/test_sparsification.py:168-220) re-run on the oracle."""
+    import scipy.sparse as sp
+
+    tri = sp.csr_matrix(np.array([[0, 1, 1], [1, 0, 1], [1, 1, 0]]))
+    s = co.calculate_jaccard_scores(tri)
+    assert np.all(s >= 0) and np.all(s <= 1)
+    iso = sp.csr_matrix(np.array([[0, 1, 0], [1, 0, 0], [0, 0, 0]]))
+    assert np.all(np.isfinite(co.calculate_jaccard_scores(iso)))
+    star = sp.csr_matrix(np.array([[0, 1, 1, 1], [1, 0, 0, 0], [1, 0, 0, 0], [1, 0, 0, 0]]))
+    assert np.all(np.isfinite(co.calculate_adamic_adar_scores(star)))
+    assert np.all(co.calculate_approx_effective_resistance_scores(tri) > 0)
