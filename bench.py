@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the edge-scoring sparsification hot path (BASELINE.json metric: edges scored/sec per method).
+
+    python bench.py --gpus N --steps K --warmup W                 (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                           (the reference's CPU path, oracle port, host cores)
+
+A *step* is one pass of the hot path over the whole synthetic graph: Jaccard, Adamic-Adar and feature-cosine
+scoring of every directed edge, each followed by global top-50 % selection (radix select) and edge_index
+compaction. Units per step = 3 x E edge scores.
+
+  value  device-timed: graph CSR + features already resident in HBM, CUDA events around the K steps, max over ranks.
+  e2e    the same step through the reference-facing API (`GraphSparsifier(data, ...)`, `compute_scores`, `sparsify`)
+         with HOST inputs: pinned edge_index / features are copied H2D, the fp64 score vectors and bool masks the
+         reference API returns come back D2H, all inside the timed region.
+
+N > 1 shards the canonical edge range over the ranks (CSR + features replicated, generated identically on every
+rank): scoring needs no communication; selection all-reduces 6 x 16 KB radix histograms (NCCL). Fixed graph =>
+"scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METHODS = ("jaccard", "adamic_adar", "feature_cosine")
+RETENTION = 0.5
+CPU_SAMPLE = dict(scale=15, num_nodes=1 << 15, edges=(1 << 15) * 16, dim=128, seed=5)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_step(adj, x, e):
+    """One step of the hot path with the reference's own algorithm (oracle/scipy_port.py = its SciPy/NumPy calls)."""
+    from oracle import scipy_port as port
+
+    for m in METHODS:
+        s = port.jaccard(adj) if m == "jaccard" else port.adamic_adar(adj) if m == "adamic_adar" else port.feature_cosine(adj, x)
+        port.threshold_mask(s, e, RETENTION, stable=False)      # reference default argsort kind
+
+
+def cpu_sample_inputs():
+    from gsr_b200.synthetic import features, rmat_graph
+    from oracle import scipy_port as port
+
+    c = CPU_SAMPLE
+    ei = rmat_graph(c["num_nodes"], c["edges"], c["scale"], c["seed"])
+    x = features(c["num_nodes"], c["dim"], c["seed"])
+    return port.build_adjacency(ei, c["num_nodes"]), x, c["edges"]
+
+
+def cpu_sample_description() -> str:
+    c = CPU_SAMPLE
+    return (f"R-MAT scale {c['scale']} ({c['num_nodes']} nodes, {c['edges']} directed edges, {c['dim']}-d fp32), same generator "
+            f"family as the GPU workload; one full step (Jaccard+AA+FeatCos scoring via SciPy SpGEMM/NumPy + argsort top-50%)")
+
+
+def run_reference_arm(args) -> None:
+    """`--impl reference`: the reference's CPU implementation (oracle port; the reference is pure Python and
+    /root/reference is absent on the GPU box) on a bounded sample of the workload, all host threads available."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    adj, x, e = cpu_sample_inputs()
+    for _ in range(args.warmup):
+        cpu_port_step(adj, x, e)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(adj, x, e)
+    dt = time.perf_counter() - t0
+    value = len(METHODS) * e * args.steps / dt
+    cores = len(os.sched_getaffinity(0))
+    line = {
+        "impl": "reference", "metric": "edges scored/sec (Jaccard+AA+FeatCos scoring + top-k select)", "value": value,
+        "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
+        "config": {"workload": workload_name(args), "cpu_sample": cpu_sample_description()},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": cpu_sample_description()},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def workload_name(args) -> str:
+    return (f"rmat scale {args.scale}: {1 << args.scale} nodes, {(1 << args.scale) * args.edge_factor} directed edges, "
+            f"{args.dim}-d fp32 features; Jaccard/AA/FeatCos scoring + top-{int(RETENTION * 100)}% select + compaction")
+
+
+def balanced_ranges(graph, world: int):
+    """Contiguous canonical edge ranges with ~equal estimated intersection work (min-degree of the endpoints)."""
+    e = graph.nnz
+    if world == 1:
+        return [(0, e)]
+    indptr, indices, _, rows = graph.export(with_data=False, with_rows=True)
+    deg = (indptr[1:] - indptr[:-1])
+    cost = torch.minimum(deg[rows.long()], deg[indices.long()]).double() + 8.0
+    csum = torch.cumsum(cost, 0)
+    total = float(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(torch.searchsorted(csum, torch.tensor([total * r / world], device=csum.device, dtype=csum.dtype)).item()))
+    cuts.append(e)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=int, default=24, help="R-MAT scale (BASELINE config 5: 24)")
+    ap.add_argument("--edge-factor", type=int, default=16, help="directed edges per node (16 -> 268 M at scale 24)")
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 1)   # the driver passes W; timing rules ask for >= 3 in reported runs
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import gsr_b200
+    from gsr_b200 import _lib, engine
+    from gsr_b200.synthetic import rmat_graph_device
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    lib = _lib.load()
+
+    n = 1 << args.scale
+    e = n * args.edge_factor
+    ei = rmat_graph_device(n, e, args.scale, seed=5, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(1005)
+    x = torch.randn((n, args.dim), dtype=torch.float32, device=dev, generator=gen)
+    graph = engine.DeviceGraph(ei, n)
+    assert graph.nnz == e and graph.symmetric and graph.input_canonical
+    e_lo, e_hi = balanced_ranges(graph, world)[rank]
+    local = e_hi - e_lo
+    num_keep = int(e * RETENTION)
+    deg_table = None
+
+    scores = torch.empty(local, dtype=torch.float64, device=dev)
+    mask = torch.empty(local, dtype=torch.uint8, device=dev)
+    ei_local = ei[:, e_lo:e_hi].contiguous() if world > 1 else ei
+    ev = {m: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for m in METHODS}
+    ev_sel = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kernel_ms = {m: 0.0 for m in METHODS}
+    kernel_ms["select+compact"] = 0.0
+
+    def aa_weights():
+        # constant table of node weights per distinct degree (NumPy expression), gathered on device
+        nonlocal deg_table
+        if deg_table is None:
+            t = np.arange(graph.max_degree + 1, dtype=np.float64)
+            deg_table = torch.from_numpy(1.0 / np.sqrt(np.maximum(np.log(t + 1), 1e-10))).to(dev)
+        return deg_table[graph.degrees().long()]
+
+    def step(record: bool):
+        for m in METHODS:
+            ev[m][0].record()
+            if m == "jaccard":
+                graph.jaccard(e_lo, e_hi, out=scores)
+            elif m == "adamic_adar":
+                graph.adamic_adar(aa_weights(), e_lo, e_hi, out=scores)
+            else:
+                xhat = graph.normalize_features(x)
+                graph.feature_cosine(xhat, e_lo, e_hi, out=scores)
+                del xhat
+            ev[m][1].record()
+            ev_sel[0].record()
+            if world > 1:
+                engine.select_mask_sharded(scores, num_keep, False, group, out=mask)
+                kept_local = int(mask.sum().item())
+            else:
+                engine.select_mask(scores, num_keep, False, out=mask)
+                kept_local = num_keep
+            engine.compact_edges(ei_local, mask, kept_local)
+            ev_sel[1].record()
+            if record:
+                torch.cuda.synchronize(dev)
+                kernel_ms[m] += ev[m][0].elapsed_time(ev[m][1])
+                kernel_ms["select+compact"] += ev_sel[0].elapsed_time(ev_sel[1])
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group)
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 1)):
+        step(False)
+    # pass 1: per-kernel durations (CUDA events on the launching stream, one sync per method) for the roofline
+    barrier()
+    for _ in range(args.steps):
+        step(True)
+    # pass 2: the reported number — K steps back to back, no host sync inside, max over ranks
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.gsp_launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        step(False)
+    t_end.record()
+    barrier()
+    launches = lib.gsp_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX, group=group)
+        for k in kernel_ms:
+            t = torch.tensor([kernel_ms[k]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            kernel_ms[k] = float(t)
+    ms_per_step = float(elapsed_ms) / args.steps
+    value = len(METHODS) * e / (ms_per_step * 1e-3)
+
+    # ---- e2e through the reference-facing API, host inputs (rank-local replica; N>1 repeats it per rank) ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        ei_host = ei.cpu().pin_memory()
+        x_host = x.cpu().pin_memory()
+        h2d = ei_host.numel() * 8 + x_host.numel() * 4
+        d2h = 0
+        times = []
+        for it in range(1 + args.e2e_steps):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n)
+            sp = gsr_b200.GraphSparsifier(data, str(dev))
+            d2h = 0
+            for m in METHODS:
+                s = sp.compute_scores(m)                                  # np.ndarray fp64 on host
+                out, msk = sp.sparsify(m, RETENTION, return_mask=True)    # Data (edge_index on device) + host bool mask
+                d2h += s.nbytes + msk.numel()
+                del out, msk
+            torch.cuda.synchronize(dev)
+            if it > 0:
+                times.append(time.perf_counter() - t0)
+            del sp, data
+        e2e = {"value": len(METHODS) * e / (sum(times) / len(times)), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": sum(times) / len(times) * 1e3,
+               "api": "GraphSparsifier(data_host).compute_scores(m) + sparsify(m, 0.5, return_mask=True) for 3 metrics"}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- roofline (SURVEY §8d algorithmic bytes; peak = MEASURED_PEAKS.json hbm_gbs, fallback 6650 of B200_PROFILING.md)
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
+    except Exception:
+        pass
+    s2 = graph.sum_degree_sq
+    frac_edges = local / e
+    alg_bytes = {
+        "jaccard": (4.0 * s2 + 20.0 * e) * frac_edges,
+        "adamic_adar": (4.0 * s2 + 20.0 * e) * frac_edges,        # + 8*T (matches) not counted: lower bound
+        "feature_cosine": (4.0 * args.dim * e + 4.0 * e + 8.0 * e) * frac_edges + 12.0 * args.dim * n,
+        "select+compact": (8.0 * local * 8 + local) + 17.0 * local + 16.0 * num_keep / world,
+    }
+    per_kernel = {}
+    for k, ms in kernel_ms.items():
+        avg = ms / args.steps
+        gbs = alg_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
+        per_kernel[k] = {"ms": avg, "alg_gb": alg_bytes[k] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak,
+                         "edges_per_s": (local / (avg * 1e-3)) if k != "select+compact" else None}
+    dominant = max(METHODS, key=lambda m: kernel_ms[m])
+    roofline = {"bound": "hbm", "kernel": {"jaccard": "intersect_kernel<0>", "adamic_adar": "intersect_kernel<1>",
+                                            "feature_cosine": "featcos_kernel<float>"}[dominant],
+                "achieved": per_kernel[dominant]["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": per_kernel[dominant]["frac"], "traffic": None,
+                "note": "algorithmic bytes per SURVEY §8d; per-launch duration from CUDA events on the launching stream"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        adj, xs, es = cpu_sample_inputs()
+        t0 = time.perf_counter()
+        cpu_port_step(adj, xs, es)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": len(METHODS) * es / dt, "unit": "edges/s", "cores": 1, "kind": "port",
+                        "host_cores_available": len(os.sched_getaffinity(0)), "seconds": dt, "sample": cpu_sample_description()}
+
+    line = {
+        "metric": "edges scored/sec (Jaccard+AA+FeatCos scoring + top-k select)", "value": value, "unit": "edges/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
+        "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": graph.max_degree,
+                   "sum_degree_sq": s2, "retention": RETENTION, "l2": "inputs_larger_than_L2",
+                   "parallelism": f"edge-sharded x{world}, CSR+features replicated"},
+        "per_method": per_kernel, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,7 @@ _F64 = C.c_double
 PROTOTYPES = {
     "gsp_version": (_INT, []),
     "gsp_last_error": (C.c_char_p, []),
+    "gsp_launch_count": (C.c_uint64, []),
     "gsp_graph_create": (_INT, [_I64, _I64, _P, _P, _P, _P, C.POINTER(_P)]),
     "gsp_graph_destroy": (None, [_P]),
     "gsp_graph_get_info": (_INT, [_P, C.POINTER(GraphInfo)]),

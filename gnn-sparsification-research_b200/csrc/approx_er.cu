@@ -329,10 +329,14 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
             if (host_active <= 0) break;
         }
         top_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg, rtol, it, num_active);
+        GSP_CHECK_LAUNCH();
         direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
+        GSP_CHECK_LAUNCH();
         spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(n, g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, cg.active,
                                                    partial.ptr);
+        GSP_CHECK_LAUNCH();
         alpha_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg);
+        GSP_CHECK_LAUNCH();
         update_kernel<<<grid2d, kThreads, 0, s>>>(n, k, p.ptr, q.ptr, x.ptr, r.ptr, cg, partial.ptr);
         GSP_CHECK_LAUNCH();
     }

@@ -17,6 +17,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 constexpr int kWarp = 32;
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define GSP_CUDA_TRY(expr)                                                                              \
     do {                                                                                                \
@@ -35,7 +36,12 @@ void set_error(const char* fmt, ...);
         }                                                       \
     } while (0)
 
-#define GSP_CHECK_LAUNCH() GSP_CUDA_TRY(cudaGetLastError())
+// Placed after EVERY kernel launch: checks the launch and counts it (gsp_launch_count feeds bench.py's gpu_launches).
+#define GSP_CHECK_LAUNCH()                  \
+    do {                                    \
+        gsp::count_launch();                \
+        GSP_CUDA_TRY(cudaGetLastError());   \
+    } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -77,7 +83,17 @@ struct Graph {
     int32_t* tidx = nullptr;
     // lazily built
     int32_t* und_id = nullptr;   // [nnz]
+    void* owner_items = nullptr; // work items of the owner-hashed intersection (intersect_owner.cu)
+    int64_t num_owner_items = 0;
+    bool owner_items_ready = false;
 };
+
+// graph.cu: CUB inclusive scan wrapper shared by the lazily built side structures
+int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s);
+// intersect_owner.cu: fast path for symmetric graphs (each undirected pair evaluated once at its owner)
+int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int32_t* inter, double* score, cudaStream_t s);
+int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, double* score,
+                                cudaStream_t s);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -10,7 +10,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
-#include <mutex>
+#include <atomic>
 #include <new>
 
 #include "common.cuh"
@@ -25,6 +25,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
@@ -229,6 +232,7 @@ void free_graph(Graph* g) {
     cudaFree(g->tptr);
     cudaFree(g->tidx);
     cudaFree(g->und_id);
+    cudaFree(g->owner_items);
     delete g;
 }
 
@@ -377,6 +381,9 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
 }
 
 }  // namespace
+
+int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s) { return inclusive_sum(in, out, count, s); }
+
 }  // namespace gsp
 
 using namespace gsp;
@@ -384,6 +391,8 @@ using namespace gsp;
 GSP_API int gsp_version(void) { return GSP_VERSION; }
 
 GSP_API const char* gsp_last_error(void) { return gsp::g_error; }
+
+GSP_API uint64_t gsp_launch_count(void) { return gsp::g_launches.load(std::memory_order_relaxed); }
 
 GSP_API int gsp_graph_create(int64_t num_nodes, int64_t num_edges, const int64_t* d_row, const int64_t* d_col,
                              const double* d_val, void* stream, gsp_graph** out) {

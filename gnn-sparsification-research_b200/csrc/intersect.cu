@@ -11,6 +11,8 @@
 // Per edge the shorter list is streamed 32 ids per step (one coalesced request) and every lane
 // lower-bounds its id in the longer list; the search window shrinks monotonically because both lists
 // are sorted.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gsp {
@@ -149,9 +151,21 @@ int check_range(const Graph* g, int64_t e_begin, int64_t e_end) {
     return GSP_OK;
 }
 
+// GSP_INTERSECT=general forces the per-edge search kernel (tests cover both schedules)
+bool use_owner_path(const Graph* g) {
+    if (!g->symmetric) return false;
+    const char* env = getenv("GSP_INTERSECT");
+    return !(env && env[0] == 'g');
+}
+
 template <int kMode>
 int launch_intersect(const Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32_t* inter, double* score,
                      cudaStream_t s) {
+    if (use_owner_path(g)) {
+        Graph* gm = const_cast<Graph*>(g);
+        return kMode == 0 ? owner_intersect_jaccard(gm, e_begin, e_end, inter, score, s)
+                          : owner_intersect_adamic_adar(gm, e_begin, e_end, node_w, score, s);
+    }
     GraphView view{g->indptr, g->indices, g->rows, g->indptr, g->indices};
     if (kMode == 0 && !g->symmetric) {
         view.bptr = g->tptr;

