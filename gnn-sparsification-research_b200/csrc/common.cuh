@@ -84,7 +84,8 @@ struct Graph {
     // lazily built
     int32_t* und_id = nullptr;   // [nnz]
     void* owner_items = nullptr; // work items of the owner-hashed intersection (intersect_owner.cu)
-    int64_t num_owner_items = 0;
+    int64_t num_owner_items = 0; // medium-class items (first in the array)
+    int64_t num_hub_items = 0;   // hub-class items (after them)
     bool owner_items_ready = false;
 };
 

@@ -11,9 +11,11 @@
 // descending-id accumulation order are all symmetric in the pair).
 //
 //   level A  rows with 1 <= deg <= 64: one warp per owner, 128-slot table per warp, neighbours in registers
-//   level B  rows with deg > 64: CTA per (owner, 1024-neighbour chunk); the owner row is hashed in tiles of
-//            8192 ids (16384 slots), tiles visited in DESCENDING id order so Adamic-Adar keeps SciPy's
-//            accumulation order; per-neighbour partial state lives in shared memory between tiles
+//   level B  rows with deg > 64: CTA per (owner, neighbour chunk). Two size classes of the same kernel:
+//            64 < deg <= 1536: 256 threads, 4096 cuckoo slots, 512-neighbour chunks (~6 CTAs per SM);
+//            deg > 1536: 1024 threads, one CTA per SM, the owner row hashed in tiles of 12288 ids (32768 slots),
+//            tiles visited in DESCENDING id order so Adamic-Adar keeps SciPy's accumulation order. Neighbour
+//            metadata is fetched once per item; each neighbour keeps a cursor into its row between tiles.
 //
 // An edge range [e_begin, e_end) (multi-GPU sharding) restricts the pairs to those with a directed position
 // inside the range; only in-range positions are written.
@@ -30,12 +32,6 @@ constexpr int kATableSlots = 128;          // per-warp hash slots (load factor <
 constexpr int kAThreads = 256;
 constexpr int kAWarps = kAThreads / kWarp;
 constexpr int kARowsPerClaim = 16;
-
-constexpr int kBThreads = 512;
-constexpr int kBWarps = kBThreads / kWarp;
-constexpr int kBTile = 8192;               // owner ids per hash tile
-constexpr int kBSlots = 2 * kBTile;
-constexpr int kBChunk = 1024;              // neighbours per work item
 
 __device__ __forceinline__ uint32_t hash_id(int32_t x) { return (uint32_t)x * 0x9E3779B1u; }
 
@@ -56,6 +52,47 @@ __device__ __forceinline__ bool hash_contains(const int32_t* slots, uint32_t mas
         if (s == -1) return false;
         h = (h + 1) & mask;
     }
+}
+
+// ---- level-B membership structure: two-table cuckoo hash in shared memory --------------------------------
+// A lookup is exactly two independent shared-memory loads (no probe loop, no divergence): profiling the first
+// linear-probing version showed ~50 % of all issued instructions in its probe loop at 3-8 active lanes.
+// Keys that cannot be placed after kCuckooMaxKicks evictions go to a small stash that lookups scan only when it
+// is non-empty; if even the stash overflows the tile is rebuilt with the next pair of multipliers.
+constexpr int kCuckooMaxKicks = 64;
+constexpr int kStashMax = 32;
+
+struct Cuckoo {
+    const int32_t* t1;
+    const int32_t* t2;
+    const int32_t* stash;
+    uint32_t mul1, mul2;
+    int shift;
+    int stash_n;
+};
+
+__device__ __forceinline__ void cuckoo_insert(int32_t* t1, int32_t* t2, int shift, uint32_t mul1, uint32_t mul2, int32_t x,
+                                              int32_t* stash, int* stash_n) {
+    int which = 0;
+    for (int it = 0; it < kCuckooMaxKicks; ++it) {
+        int32_t* tab = which ? t2 : t1;
+        const uint32_t h = ((uint32_t)x * (which ? mul2 : mul1)) >> shift;
+        x = atomicExch(&tab[h], x);
+        if (x == -1) return;
+        which ^= 1;  // the evicted key moves to its slot in the other table
+    }
+    const int k = atomicAdd(stash_n, 1);
+    if (k < kStashMax) stash[k] = x;
+}
+
+__device__ __forceinline__ bool cuckoo_contains(const Cuckoo& c, int32_t x) {
+    const int32_t a = c.t1[((uint32_t)x * c.mul1) >> c.shift];
+    const int32_t b = c.t2[((uint32_t)x * c.mul2) >> c.shift];
+    bool f = (a == x) | (b == x);
+    if (c.stash_n) {
+        for (int k = 0; k < c.stash_n; ++k) f |= c.stash[k] == x;
+    }
+    return f;
 }
 
 // the pair {o, w} is evaluated at o unless w has the larger degree (ties: smaller id owns)
@@ -204,19 +241,99 @@ struct OwnerItem {
     int32_t first;  // index of the chunk's first neighbour inside the owner's row
 };
 
+// Two size classes share one kernel; the launch picks block size, hash slots and chunk length.
+struct OwnerClass {
+    int slots;      // hash slots per tile (power of two); a tile holds slots/2 owner ids
+    int chunk;      // neighbours per work item
+    int threads;
+};
+// slots = both cuckoo tables together; a tile holds at most kTileLoad * slots owner ids (load factor 0.375)
+constexpr int kMediumMaxDegree = 1536;
+constexpr OwnerClass kMediumClass{4096, 512, 256};       // 16 KB tables + 16 KB state: ~6 CTAs / SM
+constexpr OwnerClass kHubClass{32768, 2048, 1024};       // 128 KB tables + 64 KB state: 1 CTA / SM
+__host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3; }
+
+__host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c) {
+    // slots | base(int64) | acc(double) | len | cursor | rev | cnt
+    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4);
+}
+
+// Process the part of row(w) that lies in the current tile's id range [lo_id, +inf) below `cursor`, walking DOWN
+// from the cursor (ids descending: SciPy's Adamic-Adar accumulation order; Jaccard does not care). Four 32-id
+// groups are loaded per round so a long row keeps four requests in flight. Returns the new cursor.
 template <int kMode>
-__global__ void __launch_bounds__(kBThreads)
-cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ indptr,
-                 const int32_t* __restrict__ indices, RangeInfo r, const double* __restrict__ node_w,
-                 int32_t* __restrict__ inter_out, double* __restrict__ score_out, unsigned long long* counter) {
+__device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, int cursor, int32_t lo_id,
+                                           const Cuckoo& table, int32_t o,
+                                           const double* __restrict__ node_w, int& count, double& acc, int& rev) {
+    const int lane = lane_id();
+    int c = 0;
+    bool done = false;
+    while (cursor > 0 && !done) {
+        int32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = cursor - 1 - k * kWarp - lane;
+            x[k] = i >= 0 ? __ldg(row_w + i) : INT_MIN;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (done) break;
+            const int i = cursor - 1 - k * kWarp - lane;
+            const bool in_tile = i >= 0 && x[k] >= lo_id;
+            bool hit = false;
+            if (in_tile) {
+                hit = cuckoo_contains(table, x[k]);
+                if (x[k] == o) rev = i;
+            }
+            if (kMode == 0) {
+                c += hit;
+            } else {
+                double term = 0.0;
+                if (hit) {
+                    const double w = __ldg(node_w + x[k]);
+                    term = __dmul_rn(w, w);
+                }
+                unsigned hits = __ballot_sync(0xffffffffu, hit);
+                while (hits) {  // lanes ascending == ids descending
+                    const int src = __ffs(hits) - 1;
+                    acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, term, src));
+                    hits &= hits - 1;
+                }
+            }
+            const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
+            if (inside != 0xffffffffu) {            // ran off the tile (or the row): stop after this group
+                done = true;
+                cursor = cursor - k * kWarp - __popc(inside);
+            }
+        }
+        if (!done) cursor -= 4 * kWarp;
+    }
+    if (cursor < 0) cursor = 0;
+    if (kMode == 0) count += __reduce_add_sync(0xffffffffu, c);
+    rev = __reduce_max_sync(0xffffffffu, rev);
+    return cursor;
+}
+
+template <int kMode>
+__global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, OwnerClass cls,
+                                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, RangeInfo r,
+                                 const double* __restrict__ node_w, int32_t* __restrict__ inter_out,
+                                 double* __restrict__ score_out, unsigned long long* counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int32_t* slots = reinterpret_cast<int32_t*>(smem_raw);                          // [kBSlots]
-    double* acc_s = reinterpret_cast<double*>(smem_raw + sizeof(int32_t) * kBSlots);  // [kBChunk]
-    int32_t* cnt_s = reinterpret_cast<int32_t*>(acc_s + kBChunk);                   // [kBChunk]
-    int32_t* rev_s = cnt_s + kBChunk;                                               // [kBChunk]
+    int32_t* slots = reinterpret_cast<int32_t*>(smem_raw);
+    long long* base_s = reinterpret_cast<long long*>(smem_raw + sizeof(int32_t) * (size_t)cls.slots);
+    double* acc_s = reinterpret_cast<double*>(base_s + cls.chunk);
+    int32_t* len_s = reinterpret_cast<int32_t*>(acc_s + cls.chunk);   // row length, -1 = pair not evaluated here
+    int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
+    int32_t* rev_s = cur_s + cls.chunk;                               // offset of o inside row(w)
+    int32_t* cnt_s = rev_s + cls.chunk;
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
+    const int nthreads = blockDim.x;
+    const int tile_ids = tile_ids_for(cls.slots);
+    __shared__ int32_t stash_s[kStashMax];
+    __shared__ int stash_n_s;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) item_s = (long long)atomicAdd(counter, 1ull);
@@ -227,94 +344,107 @@ cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, const i
         const int j0 = items[item].first;
         const int64_t a0 = __ldg(indptr + o);
         const int d_o = (int)(__ldg(indptr + o + 1) - a0);
-        const int nb = min(kBChunk, d_o - j0);
+        const int nb = min(cls.chunk, d_o - j0);
         const int32_t* row_o = indices + a0;
         if (!r.full) {
             const int64_t c0 = a0 + j0, c1 = c0 + nb;
-            const bool chunk_in_range = c0 < r.e_end && c1 > r.e_begin;
-            if (!chunk_in_range) {
+            if (!(c0 < r.e_end && c1 > r.e_begin)) {
                 const int32_t w_first = __ldg(row_o + j0), w_last = __ldg(row_o + j0 + nb - 1);
                 if (w_last < r.row_lo || w_first > r.row_hi) continue;
             }
         }
-        for (int i = threadIdx.x; i < nb; i += kBThreads) {
-            acc_s[i] = 0.0;
-            cnt_s[i] = 0;
+        // neighbour metadata once per item: row start, length (or -1 when the pair is evaluated elsewhere)
+        for (int i = threadIdx.x; i < nb; i += nthreads) {
+            const int32_t w = __ldg(row_o + j0 + i);
+            const int64_t b0 = __ldg(indptr + w);
+            const int d_w = (int)(__ldg(indptr + w + 1) - b0);
+            bool skip = other_owns(d_w, w, d_o, o);
+            if (!skip && !r.full) {
+                const int64_t p1 = a0 + j0 + i;
+                skip = !(p1 >= r.e_begin && p1 < r.e_end) && !(b0 < r.e_end && b0 + d_w > r.e_begin);
+            }
+            base_s[i] = b0;
+            len_s[i] = skip ? -1 : d_w;
+            cur_s[i] = d_w;
             rev_s[i] = -1;
+            cnt_s[i] = 0;
+            acc_s[i] = 0.0;
         }
-        const int num_tiles = (d_o + kBTile - 1) / kBTile;
+        const int num_tiles = (d_o + tile_ids - 1) / tile_ids;
         for (int t = num_tiles - 1; t >= 0; --t) {
-            const int ts = t * kBTile, te = min(d_o, ts + kBTile);
-            int cap = 64;
-            while (cap < 2 * (te - ts)) cap <<= 1;
-            const uint32_t mask = (uint32_t)cap - 1u;
+            const int ts = t * tile_ids, te = min(d_o, ts + tile_ids);
+            int cap = 32;  // slots per table: smallest power of two with (te - ts) <= 0.75 * cap
+            while (3 * cap < 4 * (te - ts)) cap <<= 1;
             const int shift = 32 - (31 - __clz(cap));
-            __syncthreads();  // previous tile's probes are done
-            for (int i = threadIdx.x; i < cap; i += kBThreads) slots[i] = -1;
-            if (threadIdx.x == 0) next_s = 0;
-            __syncthreads();
-            for (int i = ts + threadIdx.x; i < te; i += kBThreads) hash_insert(slots, mask, shift, __ldg(row_o + i));
-            __syncthreads();
-            const int32_t lo_id = t == 0 ? INT_MIN : __ldg(row_o + ts);
-            const bool last_tile = t == num_tiles - 1;
-            const int32_t hi_id = last_tile ? INT_MAX : __ldg(row_o + te);
+            int32_t* t1 = slots;
+            int32_t* t2 = slots + cap;
+            uint32_t mul1 = 0x9E3779B1u, mul2 = 0x85EBCA77u;
+            for (;;) {
+                __syncthreads();  // previous tile's probes (and the metadata writes) are done
+                for (int i = threadIdx.x; i < 2 * cap; i += nthreads) slots[i] = -1;
+                if (threadIdx.x == 0) { next_s = 0; stash_n_s = 0; }
+                __syncthreads();
+                for (int i = ts + threadIdx.x; i < te; i += nthreads)
+                    cuckoo_insert(t1, t2, shift, mul1, mul2, __ldg(row_o + i), stash_s, &stash_n_s);
+                __syncthreads();
+                if (stash_n_s <= kStashMax) break;
+                mul1 += 0x3C6EF372u;  // stash overflow (practically never): rebuild with other multipliers (kept odd)
+                mul2 += 0x1B873592u;
+            }
+            const Cuckoo table{t1, t2, stash_s, mul1, mul2, shift, stash_n_s};
+            const int32_t lo_id = t == 0 ? INT_MIN + 1 : __ldg(row_o + ts);
             for (;;) {
                 int i = 0;
-                if (lane == 0) i = atomicAdd(&next_s, 1);
+                if (lane == 0) i = atomicAdd(&next_s, 4);
                 i = __shfl_sync(0xffffffffu, i, 0);
                 if (i >= nb) break;
-                const int32_t w = __ldg(row_o + j0 + i);
-                const int64_t b0 = __ldg(indptr + w);
-                const int d_w = (int)(__ldg(indptr + w + 1) - b0);
-                if (other_owns(d_w, w, d_o, o)) continue;
-                if (!r.full) {
-                    const int64_t p1 = a0 + j0 + i;
-                    const bool p1_in = p1 >= r.e_begin && p1 < r.e_end;
-                    const bool w_in = b0 < r.e_end && b0 + d_w > r.e_begin;
-                    if (!p1_in && !w_in) continue;
-                }
-                const int32_t* row_w = indices + b0;
-                const int s = t == 0 ? 0 : lower_bound_i32(row_w, d_w, lo_id);
-                const int e = last_tile ? d_w : lower_bound_i32(row_w, d_w, hi_id);
-                int count = 0, rev = -1;
-                double acc = kMode == 1 ? acc_s[i] : 0.0;
-                stream_row<kMode>(row_w, s, e, slots, mask, shift, o, node_w, count, acc, rev);
-                if (lane == 0) {
-                    if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
-                    if (rev >= 0) rev_s[i] = rev;
+                const int i_end = min(i + 4, nb);
+                for (; i < i_end; ++i) {
+                    const int d_w = len_s[i];
+                    const int cursor = cur_s[i];
+                    if (d_w < 0 || cursor <= 0) continue;
+                    int count = 0, rev = -1;
+                    double acc = kMode == 1 ? acc_s[i] : 0.0;
+                    const int new_cursor = stream_down<kMode>(indices + base_s[i], cursor, lo_id, table, o, node_w, count,
+                                                              acc, rev);
+                    if (lane == 0) {
+                        if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
+                        if (rev >= 0) rev_s[i] = rev;
+                        cur_s[i] = new_cursor;
+                    }
                 }
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += kBThreads) {
+        for (int i = threadIdx.x; i < nb; i += nthreads) {
             const int rev = rev_s[i];
-            if (rev < 0) continue;  // pair owned by the neighbour, or outside the range
-            const int32_t w = __ldg(row_o + j0 + i);
-            const int64_t b0 = __ldg(indptr + w);
-            const int d_w = (int)(__ldg(indptr + w + 1) - b0);
-            write_pair<kMode>(r, a0 + j0 + i, b0 + rev, d_o, d_w, cnt_s[i], acc_s[i], inter_out, score_out);
+            if (len_s[i] < 0 || rev < 0) continue;  // pair owned by the neighbour, or outside the range
+            write_pair<kMode>(r, a0 + j0 + i, base_s[i] + rev, d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
         }
     }
 }
 
-constexpr size_t kBSmemBytes = sizeof(int32_t) * kBSlots + sizeof(double) * kBChunk + 2 * sizeof(int32_t) * kBChunk;
-
 // ---- work items for level B (built once per graph) -----------------------------------------------------------
-__global__ void count_items_kernel(int64_t n, const int64_t* __restrict__ indptr, int64_t* __restrict__ counts) {
-    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t d = indptr[o + 1] - indptr[o];
-        counts[o] = d > kWarpOwnerMax ? (d + kBChunk - 1) / kBChunk : 0;
-    }
+__device__ __forceinline__ void item_counts(int64_t d, int64_t& medium, int64_t& hub) {
+    medium = (d > kWarpOwnerMax && d <= kMediumMaxDegree) ? (d + kMediumClass.chunk - 1) / kMediumClass.chunk : 0;
+    hub = d > kMediumMaxDegree ? (d + kHubClass.chunk - 1) / kHubClass.chunk : 0;
 }
 
-__global__ void fill_items_kernel(int64_t n, const int64_t* __restrict__ indptr, const int64_t* __restrict__ incl,
-                                  OwnerItem* __restrict__ items) {
+__global__ void count_items_kernel(int64_t n, const int64_t* __restrict__ indptr, int64_t* __restrict__ medium,
+                                   int64_t* __restrict__ hub) {
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+        item_counts(indptr[o + 1] - indptr[o], medium[o], hub[o]);
+}
+
+__global__ void fill_items_kernel(int64_t n, const int64_t* __restrict__ indptr, const int64_t* __restrict__ medium_incl,
+                                  const int64_t* __restrict__ hub_incl, OwnerItem* __restrict__ medium_items,
+                                  OwnerItem* __restrict__ hub_items) {
     for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t d = indptr[o + 1] - indptr[o];
-        if (d <= kWarpOwnerMax) continue;
-        const int64_t c = (d + kBChunk - 1) / kBChunk;
-        OwnerItem* dst = items + (incl[o] - c);
-        for (int64_t k = 0; k < c; ++k) dst[k] = OwnerItem{(int32_t)o, (int32_t)(k * kBChunk)};
+        int64_t m, h;
+        item_counts(indptr[o + 1] - indptr[o], m, h);
+        OwnerItem* dst = m ? medium_items + (medium_incl[o] - m) : hub_items + (hub_incl[o] - h);
+        const int chunk = m ? kMediumClass.chunk : kHubClass.chunk;
+        for (int64_t k = 0; k < m + h; ++k) dst[k] = OwnerItem{(int32_t)o, (int32_t)(k * chunk)};
     }
 }
 
@@ -328,25 +458,45 @@ std::mutex g_items_mutex;
 int ensure_items(Graph* g, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_items_mutex);
     if (g->owner_items_ready) return GSP_OK;
-    Scratch<int64_t> counts, incl;
-    GSP_CUDA_TRY(counts.alloc(g->n, s));
-    GSP_CUDA_TRY(incl.alloc(g->n, s));
-    count_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, counts.ptr);
+    Scratch<int64_t> cm, ch, im, ih;
+    GSP_CUDA_TRY(cm.alloc(g->n, s));
+    GSP_CUDA_TRY(ch.alloc(g->n, s));
+    GSP_CUDA_TRY(im.alloc(g->n, s));
+    GSP_CUDA_TRY(ih.alloc(g->n, s));
+    count_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, cm.ptr, ch.ptr);
     GSP_CHECK_LAUNCH();
-    if (int rc = inclusive_sum_i64(counts.ptr, incl.ptr, g->n, s)) return rc;
-    int64_t total = 0;
-    GSP_CUDA_TRY(cudaMemcpyAsync(&total, incl.ptr + (g->n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    if (int rc = inclusive_sum_i64(cm.ptr, im.ptr, g->n, s)) return rc;
+    if (int rc = inclusive_sum_i64(ch.ptr, ih.ptr, g->n, s)) return rc;
+    int64_t totals[2] = {0, 0};
+    GSP_CUDA_TRY(cudaMemcpyAsync(&totals[0], im.ptr + (g->n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    GSP_CUDA_TRY(cudaMemcpyAsync(&totals[1], ih.ptr + (g->n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     GSP_CUDA_TRY(cudaStreamSynchronize(s));
-    if (total > 0) {
-        OwnerItem* items = nullptr;
-        GSP_CUDA_TRY(cudaMalloc(&items, (size_t)total * sizeof(OwnerItem)));
-        fill_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, incl.ptr, items);
+    if (totals[0] + totals[1] > 0) {
+        OwnerItem* items = nullptr;   // medium items first, hub items after them
+        GSP_CUDA_TRY(cudaMalloc(&items, (size_t)(totals[0] + totals[1]) * sizeof(OwnerItem)));
+        fill_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, im.ptr, ih.ptr, items, items + totals[0]);
         GSP_CHECK_LAUNCH();
         GSP_CUDA_TRY(cudaStreamSynchronize(s));
         g->owner_items = items;
     }
-    g->num_owner_items = total;
+    g->num_owner_items = totals[0];
+    g->num_hub_items = totals[1];
     g->owner_items_ready = true;
+    return GSP_OK;
+}
+
+template <int kMode>
+int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, int ctas_per_sm, Graph* g, const RangeInfo& r,
+                 const double* node_w, int32_t* inter, double* score, unsigned long long* counter, cudaStream_t s) {
+    if (count <= 0) return GSP_OK;
+    const size_t smem = owner_smem_bytes(cls);
+    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)owner_smem_bytes(kHubClass)));
+    int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
+    if (blocks > count) blocks = count;
+    cta_owner_kernel<kMode><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
+                                                                  score, counter);
+    GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
 
@@ -367,20 +517,17 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32
         r.row_hi = h[1];
     }
     Scratch<unsigned long long> counters;
-    GSP_CUDA_TRY(counters.alloc(2, s));
-    GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 2 * sizeof(unsigned long long), s));
-    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBSmemBytes));
+    GSP_CUDA_TRY(counters.alloc(3, s));
+    GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 3 * sizeof(unsigned long long), s));
+    const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
     // hubs first: their long work items should not land in the tail
-    if (g->num_owner_items > 0) {
-        int64_t blocks = g->num_owner_items < 2ll * kNumSMs ? g->num_owner_items : 2ll * kNumSMs;
-        cta_owner_kernel<kMode><<<(int)blocks, kBThreads, kBSmemBytes, s>>>(
-            reinterpret_cast<const OwnerItem*>(g->owner_items), g->num_owner_items, g->indptr, g->indices, r, node_w, inter,
-            score, counters.ptr);
-        GSP_CHECK_LAUNCH();
-    }
+    if (int rc = launch_class<kMode>(kHubClass, items + g->num_owner_items, g->num_hub_items, 1, g, r, node_w, inter, score,
+                                     counters.ptr, s)) return rc;
+    if (int rc = launch_class<kMode>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
+                                     counters.ptr + 1, s)) return rc;
     const int64_t claims = (g->n + kARowsPerClaim - 1) / kARowsPerClaim;
     warp_owner_kernel<kMode><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, r, node_w, inter,
-                                                                            score, counters.ptr + 1);
+                                                                            score, counters.ptr + 2);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }

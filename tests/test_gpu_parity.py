@@ -206,16 +206,21 @@ def test_weighted_adjacency_approx_er_like_reference_karate_test():
 
 
 # ----------------------------------------------------------------------------- ApproxER
-@pytest.mark.parametrize("case", ["rmat", "chain"])
+@pytest.mark.parametrize("case", ["rmat", "chain_converged", "chain_capped"])
 def test_approx_er_against_oracle(case):
+    """Scores <= 1e-4 relative and >= 99.9 % kept-set agreement (north_star).
+
+    Mid-convergence CG iterates on the ill-conditioned chain graph amplify dot-product rounding chaotically (the
+    C oracle and the SciPy/BLAS port themselves differ by 5 % after 60 of ~390 iterations, 1e-13 after 20 and
+    3e-6 at convergence), so the iteration-cap path is pinned at a cap of 20 and the tolerance at convergence."""
     if case == "rmat":
         n = 3000
         ei = rmat_graph(n, 20000, 12, seed=77)
-        k, iters_cap = 48, 500
+        k, iters_cap, rtol = 48, 500, 1e-4
     else:
         n = 1500
-        ei = chain_with_shortcuts(n, 40, seed=5)          # chain-like: many columns hit the iteration cap
-        k, iters_cap = 16, 60
+        ei = chain_with_shortcuts(n, 40, seed=5)
+        k, iters_cap, rtol = (16, 500, 1e-4) if case == "chain_converged" else (16, 20, 1e-6)
     e = ei.shape[1]
     csr = co.csr_from_edge_index(ei, n)
     want, want_iters = co.calculate_approx_effective_resistance_scores(csr, k=k, max_cg_iters=iters_cap, return_iters=True)
@@ -223,11 +228,11 @@ def test_approx_er_against_oracle(case):
     from gsr_b200.metrics import _approx_er_on_graph
     got, iters = _approx_er_on_graph(sp.graph, k=k, max_cg_iters=iters_cap, return_iters=True)
     got = got.cpu().numpy()
-    np.testing.assert_allclose(got, want, rtol=1e-4)
+    np.testing.assert_allclose(got, want, rtol=rtol)
     # late CG iterations amplify rounding (BLAS vs sequential dots): counts agree to a few percent, scores to 1e-4
     assert np.abs(iters.cpu().numpy() - want_iters).max() <= max(3, 0.05 * want_iters.max())
-    if case == "chain":
-        assert iters.max().item() == iters_cap            # cap reached, partial iterate kept (metrics.py:287-288)
+    if case == "chain_capped":
+        assert iters.min().item() == iters_cap            # cap reached, partial iterate kept (metrics.py:287-288)
     sp.approx_er_options.update(k=k, max_cg_iters=iters_cap)
     for r in (0.8, 0.4):
         _, mask = sp.sparsify("approx_er", r, return_mask=True)
