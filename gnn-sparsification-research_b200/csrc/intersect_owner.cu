@@ -13,7 +13,7 @@
 //   level A  rows with 1 <= deg <= 64: one warp per owner, 128-slot table per warp, neighbours in registers
 //   level B  rows with deg > 64: CTA per (owner, neighbour chunk). Two size classes of the same kernel:
 //            64 < deg <= 1536: 256 threads, 4096 cuckoo slots, 512-neighbour chunks (~6 CTAs per SM);
-//            deg > 1536: 1024 threads, one CTA per SM, the owner row hashed in tiles of 12288 ids (32768 slots),
+//            deg > 1536: 640 threads, two CTAs per SM, the owner row hashed in tiles of 6144 ids (16384 slots),
 //            tiles visited in DESCENDING id order so Adamic-Adar keeps SciPy's accumulation order. Neighbour
 //            metadata is fetched once per item; each neighbour keeps a cursor into its row between tiles.
 //
@@ -63,13 +63,18 @@ constexpr int kCuckooMaxKicks = 64;
 constexpr int kStashMax = 32;
 
 struct Cuckoo {
-    const int32_t* t1;
-    const int32_t* t2;
-    const int32_t* stash;
+    uint32_t t1, t2;        // shared-state-space byte addresses of the two tables (explicit ld.shared, no generic loads)
     uint32_t mul1, mul2;
-    int shift;
+    int shift;              // 32 - log2(slots per table)
     int stash_n;
+    const int32_t* stash;
 };
+
+__device__ __forceinline__ int32_t lds_s32(uint32_t addr) {
+    int32_t v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 __device__ __forceinline__ void cuckoo_insert(int32_t* t1, int32_t* t2, int shift, uint32_t mul1, uint32_t mul2, int32_t x,
                                               int32_t* stash, int* stash_n) {
@@ -85,9 +90,11 @@ __device__ __forceinline__ void cuckoo_insert(int32_t* t1, int32_t* t2, int shif
     if (k < kStashMax) stash[k] = x;
 }
 
+// x may be the INT_MIN sentinel of an out-of-row lane: it never equals a stored id or the empty marker (-1).
 __device__ __forceinline__ bool cuckoo_contains(const Cuckoo& c, int32_t x) {
-    const int32_t a = c.t1[((uint32_t)x * c.mul1) >> c.shift];
-    const int32_t b = c.t2[((uint32_t)x * c.mul2) >> c.shift];
+    const uint32_t ux = (uint32_t)x;
+    const int32_t a = lds_s32(c.t1 + (((ux * c.mul1) >> (c.shift - 2)) & ~3u));
+    const int32_t b = lds_s32(c.t2 + (((ux * c.mul2) >> (c.shift - 2)) & ~3u));
     bool f = (a == x) | (b == x);
     if (c.stash_n) {
         for (int k = 0; k < c.stash_n; ++k) f |= c.stash[k] == x;
@@ -250,65 +257,82 @@ struct OwnerClass {
 // slots = both cuckoo tables together; a tile holds at most kTileLoad * slots owner ids (load factor 0.375)
 constexpr int kMediumMaxDegree = 1536;
 constexpr OwnerClass kMediumClass{4096, 512, 256};       // 16 KB tables + 16 KB state: ~6 CTAs / SM
-constexpr OwnerClass kHubClass{32768, 2048, 1024};       // 128 KB tables + 64 KB state: 1 CTA / SM
+constexpr OwnerClass kHubClass{16384, 1024, 640};        // 64 KB tables + 32 KB state: 2 CTAs / SM (register-limited)
 __host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3; }
 
-__host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c) {
-    // slots | base(int64) | acc(double) | len | cursor | rev | cnt
-    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4);
+__host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ordered_sum) {
+    // slots | base(int64) | acc(double) | len | cursor | rev | cnt | per-warp hit queues (Adamic-Adar only)
+    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4) +
+           (ordered_sum ? (size_t)(c.threads / kWarp) * kWarp * sizeof(double) : 0);
 }
 
-// Process the part of row(w) that lies in the current tile's id range [lo_id, +inf) below `cursor`, walking DOWN
-// from the cursor (ids descending: SciPy's Adamic-Adar accumulation order; Jaccard does not care). Four 32-id
-// groups are loaded per round so a long row keeps four requests in flight. Returns the new cursor.
+// Process the part of row(w) below `cursor` that lies in the current tile's id range [lo_id, +inf), walking DOWN
+// (ids descending: SciPy's Adamic-Adar accumulation order; Jaccard does not care). Four 32-id groups are loaded
+// per round so a long row keeps four requests in flight. Out-of-row lanes carry an INT_MIN sentinel that fails
+// every test, so the loop body is branch-free. kBounded = false is the owner's lowest tile (no id bound: the rest
+// of the row is consumed) — the only pass single-tile owners ever run. Returns the new cursor.
+// Ordered accumulation of one 32-id group: the hit lanes park their terms in a warp-private shared queue in
+// descending-id order, then every lane replays the queue (broadcast loads) with the sequential fp64 adds the
+// reference's SpGEMM performs. ~3 issue slots per hit instead of ~8 for a ballot/shuffle loop.
 template <int kMode>
+__device__ __forceinline__ void accumulate_hits(bool hit, int32_t x, const double* __restrict__ node_w, double* queue,
+                                                double& acc) {
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    if (hits == 0) return;
+    if (hit) {
+        const double w = __ldg(node_w + x);
+        queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
+    }
+    __syncwarp();
+    const int n = __popc(hits);
+#pragma unroll 4
+    for (int h = 0; h < n; ++h) acc = __dadd_rn(acc, queue[h]);
+    __syncwarp();
+}
+
+template <int kMode, bool kBounded>
 __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, int cursor, int32_t lo_id,
-                                           const Cuckoo& table, int32_t o,
-                                           const double* __restrict__ node_w, int& count, double& acc, int& rev) {
+                                           const Cuckoo& table, int32_t o, const double* __restrict__ node_w, double* queue,
+                                           int& count, double& acc, int& rev) {
     const int lane = lane_id();
     int c = 0;
-    bool done = false;
-    while (cursor > 0 && !done) {
-        int32_t x[4];
+    if (!kBounded) {
+        for (int top = cursor - 1 - lane; top + lane >= 0; top -= 4 * kWarp) {
+            int32_t x[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = cursor - 1 - k * kWarp - lane;
-            x[k] = i >= 0 ? __ldg(row_w + i) : INT_MIN;
-        }
+            for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (done) break;
-            const int i = cursor - 1 - k * kWarp - lane;
-            const bool in_tile = i >= 0 && x[k] >= lo_id;
-            bool hit = false;
-            if (in_tile) {
-                hit = cuckoo_contains(table, x[k]);
-                if (x[k] == o) rev = i;
-            }
-            if (kMode == 0) {
-                c += hit;
-            } else {
-                double term = 0.0;
-                if (hit) {
-                    const double w = __ldg(node_w + x[k]);
-                    term = __dmul_rn(w, w);
-                }
-                unsigned hits = __ballot_sync(0xffffffffu, hit);
-                while (hits) {  // lanes ascending == ids descending
-                    const int src = __ffs(hits) - 1;
-                    acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, term, src));
-                    hits &= hits - 1;
-                }
-            }
-            const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
-            if (inside != 0xffffffffu) {            // ran off the tile (or the row): stop after this group
-                done = true;
-                cursor = cursor - k * kWarp - __popc(inside);
+            for (int k = 0; k < 4; ++k) {
+                const bool hit = cuckoo_contains(table, x[k]);
+                if (x[k] == o) rev = top - k * kWarp;
+                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, x[k], node_w, queue, acc);
             }
         }
-        if (!done) cursor -= 4 * kWarp;
+        cursor = 0;
+    } else {
+        bool done = false;
+        while (cursor > 0 && !done) {
+            const int top = cursor - 1 - lane;
+            int32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (done) break;
+                const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
+                const bool hit = in_tile && cuckoo_contains(table, x[k]);
+                if (in_tile && x[k] == o) rev = top - k * kWarp;
+                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, x[k], node_w, queue, acc);
+                const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
+                if (inside != 0xffffffffu) {           // ran off the tile (or the row): stop after this group
+                    done = true;
+                    cursor = cursor - k * kWarp - __popc(inside);
+                }
+            }
+            if (!done) cursor -= 4 * kWarp;
+        }
+        if (cursor < 0) cursor = 0;
     }
-    if (cursor < 0) cursor = 0;
     if (kMode == 0) count += __reduce_add_sync(0xffffffffu, c);
     rev = __reduce_max_sync(0xffffffffu, rev);
     return cursor;
@@ -327,6 +351,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
     int32_t* rev_s = cur_s + cls.chunk;                               // offset of o inside row(w)
     int32_t* cnt_s = rev_s + cls.chunk;
+    double* queue = reinterpret_cast<double*>(cnt_s + cls.chunk) + (threadIdx.x >> 5) * kWarp;   // valid when kMode == 1
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
@@ -391,7 +416,8 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                 mul1 += 0x3C6EF372u;  // stash overflow (practically never): rebuild with other multipliers (kept odd)
                 mul2 += 0x1B873592u;
             }
-            const Cuckoo table{t1, t2, stash_s, mul1, mul2, shift, stash_n_s};
+            const Cuckoo table{(uint32_t)__cvta_generic_to_shared(t1), (uint32_t)__cvta_generic_to_shared(t2), mul1, mul2, shift,
+                               stash_n_s, stash_s};
             const int32_t lo_id = t == 0 ? INT_MIN + 1 : __ldg(row_o + ts);
             for (;;) {
                 int i = 0;
@@ -405,8 +431,10 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                     if (d_w < 0 || cursor <= 0) continue;
                     int count = 0, rev = -1;
                     double acc = kMode == 1 ? acc_s[i] : 0.0;
-                    const int new_cursor = stream_down<kMode>(indices + base_s[i], cursor, lo_id, table, o, node_w, count,
-                                                              acc, rev);
+                    const int32_t* row_w = indices + base_s[i];
+                    const int new_cursor =
+                        t == 0 ? stream_down<kMode, false>(row_w, cursor, lo_id, table, o, node_w, queue, count, acc, rev)
+                               : stream_down<kMode, true>(row_w, cursor, lo_id, table, o, node_w, queue, count, acc, rev);
                     if (lane == 0) {
                         if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
                         if (rev >= 0) rev_s[i] = rev;
@@ -489,9 +517,9 @@ template <int kMode>
 int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, int ctas_per_sm, Graph* g, const RangeInfo& r,
                  const double* node_w, int32_t* inter, double* score, unsigned long long* counter, cudaStream_t s) {
     if (count <= 0) return GSP_OK;
-    const size_t smem = owner_smem_bytes(cls);
+    const size_t smem = owner_smem_bytes(cls, kMode == 1);
     GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)owner_smem_bytes(kHubClass)));
+                                      (int)owner_smem_bytes(kHubClass, true)));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
     cta_owner_kernel<kMode><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
@@ -521,7 +549,7 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32
     GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 3 * sizeof(unsigned long long), s));
     const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
     // hubs first: their long work items should not land in the tail
-    if (int rc = launch_class<kMode>(kHubClass, items + g->num_owner_items, g->num_hub_items, 1, g, r, node_w, inter, score,
+    if (int rc = launch_class<kMode>(kHubClass, items + g->num_owner_items, g->num_hub_items, 2, g, r, node_w, inter, score,
                                      counters.ptr, s)) return rc;
     if (int rc = launch_class<kMode>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
                                      counters.ptr + 1, s)) return rc;
