@@ -151,23 +151,6 @@ def workload_name(args) -> str:
             f"{args.dim}-d fp32 features; Jaccard/AA/FeatCos scoring + top-{int(RETENTION * 100)}% select + compaction")
 
 
-def balanced_ranges(graph, world: int):
-    """Contiguous canonical edge ranges with ~equal estimated intersection work (min-degree of the endpoints)."""
-    e = graph.nnz
-    if world == 1:
-        return [(0, e)]
-    indptr, indices, _, rows = graph.export(with_data=False, with_rows=True)
-    deg = (indptr[1:] - indptr[:-1])
-    cost = torch.minimum(deg[rows.long()], deg[indices.long()]).double() + 8.0
-    csum = torch.cumsum(cost, 0)
-    total = float(csum[-1])
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(torch.searchsorted(csum, torch.tensor([total * r / world], device=csum.device, dtype=csum.dtype)).item()))
-    cuts.append(e)
-    return [(cuts[i], cuts[i + 1]) for i in range(world)]
-
-
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,7 +194,8 @@ def main() -> None:
     x = torch.randn((n, args.dim), dtype=torch.float32, device=dev, generator=gen)
     graph = engine.DeviceGraph(ei, n)
     assert graph.nnz == e and graph.symmetric and graph.input_canonical
-    e_lo, e_hi = balanced_ranges(graph, world)[rank]
+    from gsr_b200.sharding import balanced_edge_ranges
+    e_lo, e_hi = balanced_edge_ranges(graph, world)[rank]
     local = e_hi - e_lo
     num_keep = int(e * RETENTION)
     deg_table = None
@@ -306,7 +290,7 @@ def main() -> None:
         for it in range(1 + args.e2e_steps):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n)
+            data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n).to(dev, non_blocking=True)   # H2D from pinned host memory
             sp = gsr_b200.GraphSparsifier(data, str(dev))
             d2h = 0
             for m in METHODS:
@@ -320,7 +304,7 @@ def main() -> None:
             del sp, data
         e2e = {"value": len(METHODS) * e / (sum(times) / len(times)), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": sum(times) / len(times) * 1e3,
-               "api": "GraphSparsifier(data_host).compute_scores(m) + sparsify(m, 0.5, return_mask=True) for 3 metrics"}
+               "api": "data_host.to(cuda) -> GraphSparsifier(data, cuda) -> compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, return_mask=True) [host bool mask] for 3 metrics"}
 
     if rank != 0:
         if world > 1:
@@ -335,24 +319,41 @@ def main() -> None:
         pass
     s2 = graph.sum_degree_sq
     frac_edges = local / e
+    # Algorithmic bytes (DESIGN.md "Roofline accounting"). The owner-hashed intersection streams, for every undirected
+    # pair, only the SHORTER neighbour list: sum_pairs min(d_u, d_v) ids, plus the owner rows once (4E), neighbour
+    # metadata (16E) and the fp64 output (8E); Adamic-Adar adds one 8-byte weight gather per common neighbour.
+    # SURVEY 8d's formula (4*S2 + 20E: row(v) streamed once per directed edge) is reported beside it.
+    indptr_t, indices_t, _, rows_t = graph.export(with_data=False, with_rows=True)
+    deg_t = indptr_t[1:] - indptr_t[:-1]
+    sum_min = float(torch.minimum(deg_t[rows_t.long()], deg_t[indices_t.long()]).sum()) / 2.0
+    del indptr_t, indices_t, rows_t, deg_t
+    _, inter_t = graph.jaccard(return_counts=True)
+    common = float(inter_t.sum(dtype=torch.int64)) / 2.0
+    del inter_t
     alg_bytes = {
-        "jaccard": (4.0 * s2 + 20.0 * e) * frac_edges,
-        "adamic_adar": (4.0 * s2 + 20.0 * e) * frac_edges,        # + 8*T (matches) not counted: lower bound
+        "jaccard": (4.0 * sum_min + 28.0 * e) * frac_edges,
+        "adamic_adar": (4.0 * sum_min + 28.0 * e + 8.0 * common) * frac_edges,
         "feature_cosine": (4.0 * args.dim * e + 4.0 * e + 8.0 * e) * frac_edges + 12.0 * args.dim * n,
         "select+compact": (8.0 * local * 8 + local) + 17.0 * local + 16.0 * num_keep / world,
     }
+    survey_bytes = {"jaccard": (4.0 * s2 + 20.0 * e) * frac_edges, "adamic_adar": (4.0 * s2 + 20.0 * e + 8.0 * 2 * common) * frac_edges}
     per_kernel = {}
     for k, ms in kernel_ms.items():
         avg = ms / args.steps
         gbs = alg_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
         per_kernel[k] = {"ms": avg, "alg_gb": alg_bytes[k] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak,
                          "edges_per_s": (local / (avg * 1e-3)) if k != "select+compact" else None}
+        if k in survey_bytes:
+            per_kernel[k]["survey_formula_gb"] = survey_bytes[k] / 1e9
+            per_kernel[k]["survey_formula_frac"] = survey_bytes[k] / (avg * 1e-3) / 1e9 / peak
     dominant = max(METHODS, key=lambda m: kernel_ms[m])
-    roofline = {"bound": "hbm", "kernel": {"jaccard": "intersect_kernel<0>", "adamic_adar": "intersect_kernel<1>",
+    roofline = {"bound": "hbm", "kernel": {"jaccard": "cta_owner_kernel<0> (+warp_owner_kernel<0>)",
+                                            "adamic_adar": "cta_owner_kernel<1> (+warp_owner_kernel<1>)",
                                             "feature_cosine": "featcos_kernel<float>"}[dominant],
                 "achieved": per_kernel[dominant]["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": per_kernel[dominant]["frac"], "traffic": None,
-                "note": "algorithmic bytes per SURVEY §8d; per-launch duration from CUDA events on the launching stream"}
+                "note": "algorithmic bytes of the owner-hashed schedule (DESIGN.md); SURVEY 8d formula in per_method[*].survey_formula_frac; "
+                        "duration = CUDA events on the launching stream around the scoring call"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -369,7 +370,7 @@ def main() -> None:
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
         "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": graph.max_degree,
-                   "sum_degree_sq": s2, "retention": RETENTION, "l2": "inputs_larger_than_L2",
+                   "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
                    "parallelism": f"edge-sharded x{world}, CSR+features replicated"},
         "per_method": per_kernel, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,

@@ -187,32 +187,11 @@ def select_mask_sharded(scores: torch.Tensor, num_keep: int, keep_lowest: bool, 
                         or_into: bool = False) -> torch.Tensor:
     """Distributed radix select: `scores` is this rank's contiguous slice (rank order == position order).
 
-    Only the 16 KB histograms (all-reduce) and one tie count per rank (all-gather) cross NVLink."""
-    import torch.distributed as dist
+    Only the 16 KB histograms (all-reduce) and one tie count per rank (all-gather) cross NVLink; the protocol is
+    `sharding.distributed_select`."""
+    from .sharding import LibgspSelectOps, distributed_select
 
-    lib = _lib.load()
-    dev = scores.device
-    n = scores.numel()
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    mask = torch.empty(n, dtype=torch.uint8, device=dev) if out is None else out
-    state = torch.empty(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=dev)
-    hist = torch.empty(_lib.SELECT_BINS, dtype=torch.int64, device=dev)
-    ties = torch.zeros(1, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        s = stream_ptr(dev)
-        check(lib.gsp_select_begin(ptr(state), int(num_keep), int(bool(keep_lowest)), s))
-        for p in range(_lib.SELECT_PASSES):
-            check(lib.gsp_select_histogram(ptr(scores), n, ptr(exclude), ptr(state), p, ptr(hist), s))
-            dist.all_reduce(hist, group=group)
-            check(lib.gsp_select_pick(ptr(state), ptr(hist), p, s))
-        check(lib.gsp_select_count_ties(ptr(scores), n, ptr(exclude), ptr(state), ptr(ties), s))
-        all_ties = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_ties, ties, group=group)
-        before = all_ties[:rank].sum().reshape(1)
-        total = all_ties.sum().reshape(1)
-        check(lib.gsp_select_write_mask(ptr(scores), n, ptr(exclude), ptr(state), ptr(before), ptr(total),
-                                        int(bool(or_into)), ptr(mask), s))
-    return mask
+    return distributed_select(LibgspSelectOps(scores, exclude, out, or_into), num_keep, keep_lowest, group)
 
 
 def degree_aware_guarantee(src: torch.Tensor, scores: torch.Tensor, num_nodes: int, min_per_node: int):

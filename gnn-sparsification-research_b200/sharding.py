@@ -1,0 +1,175 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink on the box, gloo in CPU tests).
+
+The path shards naturally, so there is no data-path collective in scoring:
+
+  * scoring      every rank holds the replicated CSR (+ features) and scores one contiguous range of canonical
+                 edges, balanced by estimated intersection work;
+  * selection    distributed radix select: per pass each rank histograms its slice, the 2048-bin histogram is
+                 all-reduced (16 KB), every rank picks the same digit; one all-gather of per-rank tie counts
+                 resolves the (score, position) boundary; each rank writes its mask slice;
+  * ApproxER     projection columns are split over ranks, the per-edge partial sums are all-reduced;
+  * outputs      kept edge_index / mask slices are all-gathered (rank order == position order).
+
+The collective protocol lives here, independent of where the local work runs: `distributed_select` drives any
+object with the five local operations of `SelectOps` — `LibgspSelectOps` (CUDA, libgsp.so) on a GPU box, a NumPy
+stand-in with the same contract in the world_size-2 gloo tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+# ------------------------------------------------------------------------------------------ partitioning
+def balanced_cuts(cost_prefix: torch.Tensor, world: int) -> List[int]:
+    """Cut points of `world` contiguous ranges with ~equal cost; `cost_prefix` is the inclusive prefix sum."""
+    n = cost_prefix.numel()
+    if n == 0:
+        return [0] * (world + 1)
+    total = cost_prefix[-1].item()
+    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=cost_prefix.dtype, device=cost_prefix.device)
+    inner = torch.searchsorted(cost_prefix, targets).tolist() if world > 1 else []
+    cuts = [0] + [int(c) for c in inner] + [n]
+    for i in range(1, len(cuts)):           # monotone even for degenerate costs
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts
+
+
+def balanced_edge_ranges(graph, world: int) -> List[Tuple[int, int]]:
+    """Contiguous canonical-edge ranges with ~equal estimated work (min endpoint degree + a constant per edge)."""
+    if world == 1:
+        return [(0, graph.nnz)]
+    indptr, indices, _, rows = graph.export(with_data=False, with_rows=True)
+    deg = indptr[1:] - indptr[:-1]
+    cost = torch.minimum(deg[rows.long()], deg[indices.long()]).double() + 8.0
+    cuts = balanced_cuts(torch.cumsum(cost, 0), world)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def column_slice(k: int, rank: int, world: int) -> Tuple[int, int]:
+    """Projection columns [lo, hi) of rank `rank` (ApproxER column sharding)."""
+    return (k * rank) // world, (k * (rank + 1)) // world
+
+
+# ------------------------------------------------------------------------------------------ distributed select
+class SelectOps:
+    """Local operations of the radix select on this rank's slice (see include/gsp.h, selection section)."""
+
+    passes = _lib.SELECT_PASSES
+    bins = _lib.SELECT_BINS
+
+    def begin(self, num_keep: int, keep_lowest: bool) -> None: ...
+    def histogram(self, pass_index: int) -> torch.Tensor: ...          # int64[bins] on the collective's device
+    def pick(self, pass_index: int, hist: torch.Tensor) -> None: ...
+    def count_ties(self) -> torch.Tensor: ...                           # int64[1]
+    def write_mask(self, ties_before: torch.Tensor, ties_total: torch.Tensor): ...
+
+
+def distributed_select(ops: SelectOps, num_keep: int, keep_lowest: bool, group=None):
+    """Run the select protocol; returns whatever `ops.write_mask` returns (this rank's mask slice)."""
+    world = dist.get_world_size(group) if group is not None or dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    ops.begin(num_keep, keep_lowest)
+    for p in range(ops.passes):
+        hist = ops.histogram(p)
+        if world > 1:
+            dist.all_reduce(hist, group=group)
+        ops.pick(p, hist)
+    ties = ops.count_ties()
+    if world > 1:
+        all_ties = [torch.empty_like(ties) for _ in range(world)]
+        dist.all_gather(all_ties, ties, group=group)
+        all_ties = torch.cat(all_ties)
+        before = all_ties[:rank].sum().reshape(1)
+        total = all_ties.sum().reshape(1)
+    else:
+        before, total = torch.zeros_like(ties), ties
+    return ops.write_mask(before, total)
+
+
+class LibgspSelectOps(SelectOps):
+    """The CUDA implementation: every step is one libgsp.so call on torch's current stream, no host sync."""
+
+    def __init__(self, scores: torch.Tensor, exclude: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                 or_into: bool = False):
+        self.lib = _lib.load()
+        self.scores, self.exclude, self.or_into = scores, exclude, or_into
+        self.dev = scores.device
+        self.n = scores.numel()
+        self.mask = torch.empty(self.n, dtype=torch.uint8, device=self.dev) if out is None else out
+        self.state = torch.empty(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=self.dev)
+        self.hist = torch.empty(_lib.SELECT_BINS, dtype=torch.int64, device=self.dev)
+        self.ties = torch.zeros(1, dtype=torch.int64, device=self.dev)
+
+    def _s(self):
+        return _lib.stream_ptr(self.dev)
+
+    def begin(self, num_keep, keep_lowest):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gsp_select_begin(_lib.ptr(self.state), int(num_keep), int(bool(keep_lowest)), self._s()))
+
+    def histogram(self, p):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gsp_select_histogram(_lib.ptr(self.scores), self.n, _lib.ptr(self.exclude),
+                                                     _lib.ptr(self.state), p, _lib.ptr(self.hist), self._s()))
+        return self.hist
+
+    def pick(self, p, hist):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gsp_select_pick(_lib.ptr(self.state), _lib.ptr(hist), p, self._s()))
+
+    def count_ties(self):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gsp_select_count_ties(_lib.ptr(self.scores), self.n, _lib.ptr(self.exclude),
+                                                      _lib.ptr(self.state), _lib.ptr(self.ties), self._s()))
+        return self.ties
+
+    def write_mask(self, ties_before, ties_total):
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.gsp_select_write_mask(_lib.ptr(self.scores), self.n, _lib.ptr(self.exclude),
+                                                      _lib.ptr(self.state), _lib.ptr(ties_before.contiguous()),
+                                                      _lib.ptr(ties_total.contiguous()), int(self.or_into),
+                                                      _lib.ptr(self.mask), self._s()))
+        return self.mask
+
+
+# ------------------------------------------------------------------------------------------ gathers
+def all_gather_variable(local: torch.Tensor, group=None, dim: int = -1) -> torch.Tensor:
+    """Concatenate per-rank tensors of different length along `dim` in rank order (== canonical position order)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    dim = dim % local.dim()
+    count = torch.tensor([local.size(dim)], dtype=torch.int64, device=local.device)
+    counts = [torch.empty_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    sizes = [int(c.item()) for c in counts]
+    width = max(sizes)
+    moved = local.movedim(dim, 0).contiguous()
+    padded = torch.zeros((width,) + tuple(moved.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: moved.size(0)] = moved
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    out = torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+    return out.movedim(0, dim)
+
+
+def sharded_threshold_sparsify(graph, edge_index: torch.Tensor, local_scores: torch.Tensor, e_range: Tuple[int, int],
+                               num_keep: int, keep_lowest: bool, group=None, with_weights: bool = False):
+    """Global top-/bottom-`num_keep` over score slices held by the ranks of `group`.
+
+    Returns (kept edge_index [2, K] gathered on every rank, local uint8 mask slice). `with_weights` is not
+    offered here: the "-W" min-max needs global extrema (two more scalar all-reduces) — see DESIGN.md."""
+    from .engine import compact_edges
+
+    ops = LibgspSelectOps(local_scores)
+    mask = distributed_select(ops, num_keep, keep_lowest, group)
+    kept_local = int(mask.sum().item())
+    lo, hi = e_range
+    local_ei = edge_index[:, lo:hi].contiguous()
+    kept, _, _ = compact_edges(local_ei, mask, kept_local)
+    return all_gather_variable(kept, group, dim=1), mask

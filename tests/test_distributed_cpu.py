@@ -1,0 +1,128 @@
+"""world_size-2 gloo tests (CPU) of the N > 1 host logic: the distributed radix-select protocol, the variable-length
+gathers and the partitioning helpers. The local select operations are NumPy stand-ins with the contract of
+include/gsp.h (test infrastructure); on a GPU box the same protocol drives libgsp.so (tests/test_gpu_parity.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gsr_b200 import sharding
+
+SHIFTS = (53, 42, 31, 20, 9, 0)
+BITS = (11, 11, 11, 11, 11, 9)
+
+
+def ordered_keys(scores: np.ndarray) -> np.ndarray:
+    s = np.where(scores == 0.0, 0.0, scores)                     # -0.0 ties with +0.0
+    b = s.view(np.uint64)
+    neg = (b >> np.uint64(63)).astype(bool)
+    return np.where(neg, ~b, b | np.uint64(1 << 63))
+
+
+class NumpySelectOps(sharding.SelectOps):
+    def __init__(self, scores: np.ndarray):
+        self.scores = scores
+
+    def begin(self, num_keep, keep_lowest):
+        k = ordered_keys(self.scores)
+        self.keys = k if keep_lowest else ~k
+        self.keep_lowest, self.remaining, self.prefix, self.empty = keep_lowest, int(num_keep), np.uint64(0), num_keep <= 0
+
+    def _live(self, p):
+        hi = SHIFTS[p] + BITS[p]
+        if hi >= 64:
+            return np.ones(len(self.keys), bool)
+        return (self.keys >> np.uint64(hi)) == (self.prefix >> np.uint64(hi))
+
+    def histogram(self, p):
+        digits = ((self.keys[self._live(p)] >> np.uint64(SHIFTS[p])) & np.uint64((1 << BITS[p]) - 1)).astype(np.int64)
+        return torch.from_numpy(np.bincount(digits, minlength=self.bins).astype(np.int64))
+
+    def pick(self, p, hist):
+        if self.empty:
+            return
+        h = hist.numpy()
+        want = min(self.remaining, int(h.sum()))
+        csum = np.cumsum(h)
+        d = int(np.searchsorted(csum, want, side="left"))
+        self.prefix |= np.uint64(d) << np.uint64(SHIFTS[p])
+        self.remaining = want - int(csum[d] - h[d])
+
+    def count_ties(self):
+        return torch.tensor([0 if self.empty else int((self.keys == self.prefix).sum())], dtype=torch.int64)
+
+    def write_mask(self, before, total):
+        if self.empty:
+            return np.zeros(len(self.keys), bool)
+        tie = self.keys == self.prefix
+        rank = int(before) + np.cumsum(tie) - 1
+        lo, hi = (0, self.remaining) if self.keep_lowest else (int(total) - self.remaining, int(total))
+        return (self.keys < self.prefix) | (tie & (rank >= lo) & (rank < hi))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, scores, cut, cases, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = (0, cut) if rank == 0 else (cut, len(scores))
+        results = []
+        for num_keep, keep_lowest in cases:
+            mask = sharding.distributed_select(NumpySelectOps(scores[lo:hi].copy()), num_keep, keep_lowest)
+            gathered = sharding.all_gather_variable(torch.from_numpy(mask.astype(np.uint8)))
+            results.append(gathered.numpy().astype(bool))
+        # variable-length gather of [2, K] edge lists keeps rank order
+        local = torch.arange(2 * (3 + 2 * rank)).reshape(2, -1) + 100 * rank
+        ei = sharding.all_gather_variable(local, dim=1)
+        if rank == 0:
+            out.put((results, ei.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["ties", "normal", "signed_zero"])
+def test_distributed_select_protocol_world2(kind):
+    rng = np.random.default_rng(5)
+    n = 5000
+    scores = {"ties": rng.integers(0, 5, n).astype(np.float64) / 4.0,
+              "normal": rng.standard_normal(n),
+              "signed_zero": np.where(rng.random(n) < 0.5, -0.0, 0.0) + (rng.random(n) < 0.1)}[kind]
+    cases = [(0, False), (1, True), (n // 3, False), (n // 3, True), (n - 1, False), (n, True), (1234, False)]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, scores, 1777, cases, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results, ei = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    order = np.argsort(scores, kind="stable")
+    for (num_keep, keep_lowest), got in zip(cases, results):
+        want = np.zeros(n, bool)
+        want[order[:num_keep] if keep_lowest else order[n - num_keep:]] = True
+        assert np.array_equal(got, want), (kind, num_keep, keep_lowest)
+    assert ei.shape == (2, 8) and ei[0].tolist() == [0, 1, 2, 100, 101, 102, 103, 104]
+
+
+def test_partition_helpers():
+    cost = torch.tensor([1.0, 1, 1, 1, 10, 1, 1, 1, 1, 1]).cumsum(0)
+    cuts = sharding.balanced_cuts(cost, 2)
+    assert cuts[0] == 0 and cuts[-1] == 10 and 3 <= cuts[1] <= 5
+    assert sharding.balanced_cuts(torch.zeros(0), 4) == [0, 0, 0, 0, 0]
+    cuts = sharding.balanced_cuts(torch.ones(7).cumsum(0), 8)
+    assert cuts == sorted(cuts) and cuts[-1] == 7
+    slices = [sharding.column_slice(64, r, 8) for r in range(8)]
+    assert slices[0] == (0, 8) and slices[-1] == (56, 64)
+    slices = [sharding.column_slice(10, r, 4) for r in range(4)]
+    assert sum(hi - lo for lo, hi in slices) == 10 and all(a[1] == b[0] for a, b in zip(slices, slices[1:]))

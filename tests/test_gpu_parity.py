@@ -407,3 +407,33 @@ def test_edge_range_shards_reassemble_to_the_full_result(schedule, monkeypatch):
         assert torch.equal(torch.cat(parts), full[name]), name
     csr = co.csr_from_edge_index(ei, n)
     assert bits_equal(full["jaccard"].cpu().numpy(), co.calculate_jaccard_scores(csr))
+
+
+# ----------------------------------------------------------------------------- sharded select on one GPU
+def test_phased_select_with_emulated_shards():
+    """The phased C-ABI select (histogram / pick / count_ties / write_mask) on three slices of one vector, with the
+    all-reduce and the tie all-gather done by hand — the exact call sequence `sharding.distributed_select` issues
+    per rank over NCCL — must reproduce the single-shot stable-argsort mask."""
+    from gsr_b200.sharding import LibgspSelectOps
+
+    rng = np.random.default_rng(9)
+    n = 300000
+    for scores in (rng.integers(0, 3, n).astype(np.float64), rng.standard_normal(n)):
+        cuts = [0, 70001, 70002, 211111, n]
+        t = torch.from_numpy(scores).to(DEV)
+        order = np.argsort(scores, kind="stable")
+        for keep, kl in ((n // 2, False), (n // 2, True), (5, False), (n - 7, True)):
+            shards = [LibgspSelectOps(t[cuts[i]:cuts[i + 1]]) for i in range(len(cuts) - 1)]
+            for ops in shards:
+                ops.begin(keep, kl)
+            for p in range(ops.passes):
+                total = sum(ops.histogram(p).clone() for ops in shards)          # "all-reduce"
+                for ops in shards:
+                    ops.pick(p, total)
+            ties = [ops.count_ties().clone() for ops in shards]                   # "all-gather"
+            tot = torch.stack(ties).sum(0)
+            got = torch.cat([ops.write_mask(torch.stack(ties[:i]).sum(0) if i else torch.zeros_like(tot), tot)
+                             for i, ops in enumerate(shards)]).cpu().numpy().astype(bool)
+            want = np.zeros(n, bool)
+            want[order[:keep] if kl else order[n - keep:]] = True
+            assert np.array_equal(got, want), (keep, kl)
