@@ -14,7 +14,9 @@ compaction. Units per step = 3 x E edge scores.
          reference API returns come back D2H, all inside the timed region.
 
 N > 1 shards the canonical edge range over the ranks (CSR + features replicated, generated identically on every
-rank): scoring needs no communication; selection all-reduces 6 x 16 KB radix histograms (NCCL). Fixed graph =>
+rank). FeatCos scores a contiguous edge slice per rank (no communication). Jaccard / Adamic-Adar are owner-sharded:
+every undirected pair is evaluated on exactly one rank and the fp64 score vector is reduce-scattered (NCCL over
+NVLink) so each rank ends up with its slice. Selection all-reduces 6 x 16 KB radix histograms. Fixed graph =>
 "scaling": "strong".
 """
 from __future__ import annotations
@@ -194,13 +196,16 @@ def main() -> None:
     x = torch.randn((n, args.dim), dtype=torch.float32, device=dev, generator=gen)
     graph = engine.DeviceGraph(ei, n)
     assert graph.nnz == e and graph.symmetric and graph.input_canonical
-    from gsr_b200.sharding import balanced_edge_ranges
-    e_lo, e_hi = balanced_edge_ranges(graph, world)[rank]
+    from gsr_b200 import sharding
+    slice_len, slices = sharding.equal_slices(e, world)     # every rank's contiguous slice of canonical positions
+    e_lo, e_hi = slices[rank]
     local = e_hi - e_lo
+    node_range = sharding.owner_node_ranges(graph, world)[rank]
+    full_scratch = torch.empty(slice_len * world, dtype=torch.float64, device=dev) if world > 1 else None
     num_keep = int(e * RETENTION)
     deg_table = None
 
-    scores = torch.empty(local, dtype=torch.float64, device=dev)
+    scores = torch.empty(slice_len if world > 1 else local, dtype=torch.float64, device=dev)
     mask = torch.empty(local, dtype=torch.uint8, device=dev)
     ei_local = ei[:, e_lo:e_hi].contiguous() if world > 1 else ei
     ev = {m: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for m in METHODS}
@@ -219,21 +224,25 @@ def main() -> None:
     def step(record: bool):
         for m in METHODS:
             ev[m][0].record()
-            if m == "jaccard":
-                graph.jaccard(e_lo, e_hi, out=scores)
+            if world > 1 and m != "feature_cosine":
+                # owner-sharded: each undirected pair evaluated on one rank, fp64 [E] reduce-scattered over NVLink
+                s_loc = sharding.owner_sharded_scores(graph, m, group, node_range, aa_weights() if m == "adamic_adar" else None,
+                                                      scratch=full_scratch)[:local]
+            elif m == "jaccard":
+                s_loc = graph.jaccard(e_lo, e_hi, out=scores[:local])
             elif m == "adamic_adar":
-                graph.adamic_adar(aa_weights(), e_lo, e_hi, out=scores)
+                s_loc = graph.adamic_adar(aa_weights(), e_lo, e_hi, out=scores[:local])
             else:
                 xhat = graph.normalize_features(x)
-                graph.feature_cosine(xhat, e_lo, e_hi, out=scores)
+                s_loc = graph.feature_cosine(xhat, e_lo, e_hi, out=scores[:local])
                 del xhat
             ev[m][1].record()
             ev_sel[0].record()
             if world > 1:
-                engine.select_mask_sharded(scores, num_keep, False, group, out=mask)
+                engine.select_mask_sharded(s_loc, num_keep, False, group, out=mask)
                 kept_local = int(mask.sum().item())
             else:
-                engine.select_mask(scores, num_keep, False, out=mask)
+                engine.select_mask(s_loc, num_keep, False, out=mask)
                 kept_local = num_keep
             engine.compact_edges(ei_local, mask, kept_local)
             ev_sel[1].record()
@@ -371,7 +380,7 @@ def main() -> None:
         "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
         "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": graph.max_degree,
                    "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
-                   "parallelism": f"edge-sharded x{world}, CSR+features replicated"},
+                   "parallelism": f"x{world}: owner-sharded Jaccard/AA + reduce-scatter, edge-sliced FeatCos/select, CSR+features replicated"},
         "per_method": per_kernel, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }

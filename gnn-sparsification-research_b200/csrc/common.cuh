@@ -92,9 +92,11 @@ struct Graph {
 // graph.cu: CUB inclusive scan wrapper shared by the lazily built side structures
 int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s);
 // intersect_owner.cu: fast path for symmetric graphs (each undirected pair evaluated once at its owner)
-int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int32_t* inter, double* score, cudaStream_t s);
-int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, double* score,
-                                cudaStream_t s);
+int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
+                            double* score, cudaStream_t s);
+int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
+                                const double* node_w, double* score, cudaStream_t s);
+int owner_costs(const Graph* g, double* cost, cudaStream_t s);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

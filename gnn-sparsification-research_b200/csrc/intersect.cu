@@ -163,8 +163,8 @@ int launch_intersect(const Graph* g, int64_t e_begin, int64_t e_end, const doubl
                      cudaStream_t s) {
     if (use_owner_path(g)) {
         Graph* gm = const_cast<Graph*>(g);
-        return kMode == 0 ? owner_intersect_jaccard(gm, e_begin, e_end, inter, score, s)
-                          : owner_intersect_adamic_adar(gm, e_begin, e_end, node_w, score, s);
+        return kMode == 0 ? owner_intersect_jaccard(gm, e_begin, e_end, 0, g->n, inter, score, s)
+                          : owner_intersect_adamic_adar(gm, e_begin, e_end, 0, g->n, node_w, score, s);
     }
     GraphView view{g->indptr, g->indices, g->rows, g->indptr, g->indices};
     if (kMode == 0 && !g->symmetric) {
@@ -233,4 +233,43 @@ GSP_API int gsp_degree_product(const gsp_graph* gg, int64_t e_begin, int64_t e_e
     degree_product_kernel<<<grid_for(e_end - e_begin, 256), 256, 0, s>>>(e_begin, e_end, g->rows, g->indices, deg.ptr, d_score);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
+}
+
+// ---- owner-sharded variants (multi-GPU): every undirected pair is evaluated on exactly one rank -----------------
+static int check_owned(const Graph* g, int64_t node_begin, int64_t node_end, const void* out) {
+    GSP_REQUIRE(g != nullptr, "graph is NULL");
+    GSP_REQUIRE(node_begin >= 0 && node_begin <= node_end && node_end <= g->n, "owner range outside [0, num_nodes]");
+    GSP_REQUIRE(g->nnz == 0 || out != nullptr, "output is NULL");
+    if (!g->symmetric) {
+        set_error("owner-sharded scoring needs a symmetric adjacency pattern; shard by edge range instead");
+        return GSP_ERR_UNSUPPORTED;
+    }
+    return GSP_OK;
+}
+
+GSP_API int gsp_jaccard_owned(const gsp_graph* gg, int64_t node_begin, int64_t node_end, int32_t* d_inter_full,
+                              double* d_score_full, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_owned(g, node_begin, node_end, d_score_full)) return rc;
+    return owner_intersect_jaccard(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_inter_full, d_score_full,
+                                   as_stream(stream));
+}
+
+GSP_API int gsp_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                  double* d_score_full, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_owned(g, node_begin, node_end, d_score_full)) return rc;
+    cudaStream_t s = as_stream(stream);
+    Scratch<double> w;
+    if (!d_node_w) {
+        GSP_CUDA_TRY(w.alloc(g->n, s));
+        if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
+        d_node_w = w.ptr;
+    }
+    return owner_intersect_adamic_adar(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, d_score_full, s);
+}
+
+GSP_API int gsp_owner_costs(const gsp_graph* gg, double* d_cost, void* stream) {
+    GSP_REQUIRE(gg && d_cost, "NULL argument");
+    return owner_costs(reinterpret_cast<const Graph*>(gg), d_cost, as_stream(stream));
 }

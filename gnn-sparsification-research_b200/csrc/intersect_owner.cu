@@ -120,6 +120,7 @@ struct RangeInfo {
     int64_t e_begin, e_end;
     int32_t row_lo, row_hi;   // rows holding the first / last position of the range
     bool full;
+    int32_t owner_lo, owner_hi;  // only pairs owned by nodes in [owner_lo, owner_hi) are evaluated (owner sharding)
 };
 
 // Stream row(w)[s, e) through the hash table. kMode 0: returns the number of hits. kMode 1: continues the
@@ -200,8 +201,9 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
         unsigned long long first = 0;
         if (lane == 0) first = atomicAdd(counter, (unsigned long long)kARowsPerClaim);
         first = __shfl_sync(0xffffffffu, first, 0);
-        if ((int64_t)first >= n) break;
-        const int64_t last = min((int64_t)first + kARowsPerClaim, n);
+        first += (unsigned long long)r.owner_lo;
+        if ((int64_t)first >= r.owner_hi) break;
+        const int64_t last = min((int64_t)first + kARowsPerClaim, (int64_t)r.owner_hi);
         for (int64_t o64 = (int64_t)first; o64 < last; ++o64) {
             const int32_t o = (int32_t)o64;
             const int64_t a0 = __ldg(indptr + o), a1 = __ldg(indptr + o + 1);
@@ -366,6 +368,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
         const int64_t item = item_s;
         if (item >= num_items) break;
         const int32_t o = items[item].owner;
+        if (o < r.owner_lo || o >= r.owner_hi) continue;
         const int j0 = items[item].first;
         const int64_t a0 = __ldg(indptr + o);
         const int d_o = (int)(__ldg(indptr + o + 1) - a0);
@@ -529,10 +532,11 @@ int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, i
 }
 
 template <int kMode>
-int launch(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32_t* inter, double* score, cudaStream_t s) {
-    if (g->n == 0 || e_end == e_begin) return GSP_OK;
+int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w, int32_t* inter,
+           double* score, cudaStream_t s) {
+    if (g->n == 0 || e_end == e_begin || owner_hi <= owner_lo) return GSP_OK;
     if (int rc = ensure_items(g, s)) return rc;
-    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz};
+    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi};
     if (!r.full) {
         Scratch<int32_t> rr;
         GSP_CUDA_TRY(rr.alloc(2, s));
@@ -553,7 +557,7 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32
                                      counters.ptr, s)) return rc;
     if (int rc = launch_class<kMode>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
                                      counters.ptr + 1, s)) return rc;
-    const int64_t claims = (g->n + kARowsPerClaim - 1) / kARowsPerClaim;
+    const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
     warp_owner_kernel<kMode><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, r, node_w, inter,
                                                                             score, counters.ptr + 2);
     GSP_CHECK_LAUNCH();
@@ -562,13 +566,41 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, int32
 
 }  // namespace
 
-int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int32_t* inter, double* score, cudaStream_t s) {
-    return launch<0>(g, e_begin, e_end, nullptr, inter, score, s);
+// Estimated streaming work of every owner: ids of the owned neighbours' rows + a constant per neighbour.
+__global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                  double* __restrict__ cost) {
+    const int lane = lane_id();
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t o = warp; o < n; o += nwarps) {
+        const int64_t a0 = indptr[o], a1 = indptr[o + 1];
+        const int d_o = (int)(a1 - a0);
+        double c = 0.0;
+        for (int64_t p = a0 + lane; p < a1; p += kWarp) {
+            const int32_t w = __ldg(indices + p);
+            const int d_w = (int)(__ldg(indptr + w + 1) - __ldg(indptr + w));
+            c += other_owns(d_w, w, d_o, (int32_t)o) ? 2.0 : (double)d_w + 16.0;
+        }
+        for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (lane == 0) cost[o] = c + (d_o ? 8.0 : 0.0);
+    }
 }
 
-int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, const double* node_w, double* score,
-                                cudaStream_t s) {
-    return launch<1>(g, e_begin, e_end, node_w, nullptr, score, s);
+int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
+                            double* score, cudaStream_t s) {
+    return launch<0>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, s);
+}
+
+int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
+                                const double* node_w, double* score, cudaStream_t s) {
+    return launch<1>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, s);
+}
+
+int owner_costs(const Graph* g, double* cost, cudaStream_t s) {
+    if (g->n == 0) return GSP_OK;
+    owner_cost_kernel<<<grid_for(g->n, 8, 8), 256, 0, s>>>(g->n, g->indptr, g->indices, cost);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
 }
 
 }  // namespace gsp

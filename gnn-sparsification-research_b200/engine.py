@@ -120,6 +120,25 @@ class DeviceGraph:
             check(self._lib.gsp_adamic_adar(self._handle, ptr(node_weights), b, e, ptr(score), self._stream()))
         return score
 
+    # -- owner-sharded scoring (multi-GPU; see sharding.py) -------------------------------------------
+    def owner_costs(self) -> torch.Tensor:
+        cost = self._empty(self.num_nodes, torch.float64)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_owner_costs(self._handle, ptr(cost), self._stream()))
+        return cost
+
+    def jaccard_owned(self, node_begin: int, node_end: int, out: torch.Tensor, counts: Optional[torch.Tensor] = None):
+        """Scores of the pairs owned by nodes [node_begin, node_end) into the full-length (>= nnz) buffer `out`."""
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_jaccard_owned(self._handle, int(node_begin), int(node_end), ptr(counts), ptr(out), self._stream()))
+        return out
+
+    def adamic_adar_owned(self, node_weights: Optional[torch.Tensor], node_begin: int, node_end: int, out: torch.Tensor):
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_adamic_adar_owned(self._handle, ptr(node_weights), int(node_begin), int(node_end), ptr(out),
+                                                  self._stream()))
+        return out
+
     def degree_product(self, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         score = self._empty(e - b, torch.float64) if out is None else out

@@ -1,9 +1,12 @@
 """Multi-GPU plumbing: one process per GPU, `torch.distributed` (NCCL over NVLink on the box, gloo in CPU tests).
 
-The path shards naturally, so there is no data-path collective in scoring:
+The path shards naturally:
 
-  * scoring      every rank holds the replicated CSR (+ features) and scores one contiguous range of canonical
-                 edges, balanced by estimated intersection work;
+  * scoring      every rank holds the replicated CSR (+ features). FeatCos / degree score one contiguous range of
+                 canonical edges per rank with no communication. Jaccard / Adamic-Adar on a symmetric graph are
+                 owner-sharded so no pair is evaluated twice: rank r evaluates the pairs owned by its node range
+                 (balanced by `gsp_owner_costs`), writes both directed positions into a zero-filled full-length
+                 buffer, and one reduce-scatter hands every rank its slice (asymmetric graphs: edge ranges);
   * selection    distributed radix select: per pass each rank histograms its slice, the 2048-bin histogram is
                  all-reduced (16 KB), every rank picks the same digit; one all-gather of per-rank tie counts
                  resolves the (score, position) boundary; each rank writes its mask slice;
@@ -48,6 +51,41 @@ def balanced_edge_ranges(graph, world: int) -> List[Tuple[int, int]]:
     cost = torch.minimum(deg[rows.long()], deg[indices.long()]).double() + 8.0
     cuts = balanced_cuts(torch.cumsum(cost, 0), world)
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def equal_slices(count: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """(slice length L, [(lo, hi)] per rank) with L = ceil(count / world): the layout `reduce_scatter_tensor` produces."""
+    length = (count + world - 1) // world if world > 0 else count
+    return length, [(min(r * length, count), min((r + 1) * length, count)) for r in range(world)]
+
+
+def owner_node_ranges(graph, world: int) -> List[Tuple[int, int]]:
+    """Contiguous node ranges with ~equal intersection work (`gsp_owner_costs`): rank r evaluates the pairs they own."""
+    if world == 1:
+        return [(0, graph.num_nodes)]
+    cuts = balanced_cuts(torch.cumsum(graph.owner_costs(), 0), world)
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def owner_sharded_scores(graph, metric: str, group, node_range: Tuple[int, int], node_weights=None,
+                         scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Jaccard / Adamic-Adar on `world` GPUs without duplicated work: this rank evaluates the undirected pairs owned by
+    its node range, writes each score at both directed positions of a zero-filled full-length buffer, and a
+    reduce-scatter (sum; every position has exactly one non-zero contributor, so the sum is exact) hands every
+    rank its contiguous slice of `equal_slices(nnz, world)`. NCCL over NVLink; fp64 [nnz] crosses the fabric once."""
+    world = dist.get_world_size(group)
+    length, _ = equal_slices(graph.nnz, world)
+    full = scratch if scratch is not None else torch.empty(length * world, dtype=torch.float64, device=graph.device)
+    full.zero_()
+    if metric == "jaccard":
+        graph.jaccard_owned(node_range[0], node_range[1], full)
+    elif metric == "adamic_adar":
+        graph.adamic_adar_owned(node_weights, node_range[0], node_range[1], full)
+    else:
+        raise ValueError(metric)
+    out = torch.empty(length, dtype=torch.float64, device=graph.device)
+    dist.reduce_scatter_tensor(out, full, group=group)
+    return out
 
 
 def column_slice(k: int, rank: int, world: int) -> Tuple[int, int]:

@@ -98,6 +98,18 @@ int gsp_adamic_adar(const gsp_graph* g, const double* d_node_w, int64_t e_begin,
                     void* stream);
 int gsp_aa_node_weights(const gsp_graph* g, double* d_node_w, void* stream);
 
+/* Owner-sharded variants for multi-GPU scoring of a SYMMETRIC graph: every undirected pair {u,v} is evaluated on
+ * exactly one rank — the one whose node range [node_begin, node_end) holds the pair's owner (the endpoint with the
+ * larger degree, ties: smaller id) — and its score is written at BOTH directed positions of full-length (nnz)
+ * output arrays; positions of pairs owned elsewhere are not touched. The caller zero-fills the arrays and
+ * reduce-scatters (sum) them over the ranks. gsp_owner_costs gives fp64[n] per-node work estimates for balancing
+ * the node ranges. GSP_ERR_UNSUPPORTED for asymmetric graphs (shard those by edge range). */
+int gsp_jaccard_owned(const gsp_graph* g, int64_t node_begin, int64_t node_end, int32_t* d_inter_full,
+                      double* d_score_full, void* stream);
+int gsp_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                          double* d_score_full, void* stream);
+int gsp_owner_costs(const gsp_graph* g, double* d_cost, void* stream);
+
 /* degree product — replaces reference core.py:167-172 (`degree` metric; raw-value row sums). */
 int gsp_degree_product(const gsp_graph* g, int64_t e_begin, int64_t e_end, double* d_score, void* stream);
 
