@@ -208,6 +208,7 @@ def main() -> None:
     scores = torch.empty(slice_len if world > 1 else local, dtype=torch.float64, device=dev)
     mask = torch.empty(local, dtype=torch.uint8, device=dev)
     ei_local = ei[:, e_lo:e_hi].contiguous() if world > 1 else ei
+    kept_out = torch.empty((2, num_keep if world == 1 else local), dtype=torch.int64, device=dev)
     ev = {m: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for m in METHODS}
     ev_sel = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kernel_ms = {m: 0.0 for m in METHODS}
@@ -240,11 +241,9 @@ def main() -> None:
             ev_sel[0].record()
             if world > 1:
                 engine.select_mask_sharded(s_loc, num_keep, False, group, out=mask)
-                kept_local = int(mask.sum().item())
             else:
                 engine.select_mask(s_loc, num_keep, False, out=mask)
-                kept_local = num_keep
-            engine.compact_edges(ei_local, mask, kept_local)
+            engine.compact_edges(ei_local, mask, kept_out.size(1), out=kept_out)   # true count stays on the device
             ev_sel[1].record()
             if record:
                 torch.cuda.synchronize(dev)

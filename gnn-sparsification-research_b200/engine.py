@@ -226,13 +226,19 @@ def degree_aware_guarantee(src: torch.Tensor, scores: torch.Tensor, num_nodes: i
 
 
 def compact_edges(edge_index: torch.Tensor, mask: torch.Tensor, num_kept: int, scores: Optional[torch.Tensor] = None,
-                  with_weights: bool = False, invert_weights: bool = False):
-    """`edge_index[:, mask]` (+ optional min-max "-W" weights) without leaving the device."""
+                  with_weights: bool = False, invert_weights: bool = False, out: Optional[torch.Tensor] = None):
+    """`edge_index[:, mask]` (+ optional min-max "-W" weights) without leaving the device.
+
+    `num_kept` is the capacity of the output (columns); the true count comes back in the third return value (device
+    int64[1]), so a caller that does not know the count can pass an upper bound and avoid a host synchronisation."""
     lib = _lib.load()
     dev = edge_index.device
     e = edge_index.size(1)
     ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
-    out = torch.empty((2, int(num_kept)), dtype=torch.int64, device=dev)
+    if out is None:
+        out = torch.empty((2, int(num_kept)), dtype=torch.int64, device=dev)
+    else:
+        num_kept = out.size(1)
     w = torch.empty(int(num_kept), dtype=torch.float32, device=dev) if with_weights else None
     count = torch.empty(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
