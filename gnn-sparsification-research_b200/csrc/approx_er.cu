@@ -133,45 +133,116 @@ direction_kernel(int64_t n, int k, const double* __restrict__ r, double* __restr
 }
 
 // q = (D - A + reg I) p for a 32-column strip, fused with the p.q column partials.
+//
+// Work items are row SEGMENTS of at most kSeg neighbours (a row of degree d has max(1, ceil(d/kSeg)) of them), one
+// warp per item, so a hub row with 10^5 neighbours is spread over hundreds of warps instead of serialising one.
+// Rows with a single segment (almost all) are finished here in csr_matvec's exact order (neighbours ascending, the
+// diagonal at its sorted position). For longer rows segment 0 parks its partial sum in q[i] and the others in
+// `segpart`; spmm_combine_kernel adds them in segment order. Indices and p values are fetched four deep.
+constexpr int kSeg = 512;
+
+struct SegItem {
+    int32_t row;
+    int32_t seg;   // segment index inside the row
+};
+
 __global__ void __launch_bounds__(kThreads)
-spmm_dot_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                const double* __restrict__ data, const double* __restrict__ diag, int k, const double* __restrict__ p,
-                double* __restrict__ q, const int* __restrict__ active, double* __restrict__ partial) {
+spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
+                const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
+                const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
+                double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
     const int c = blockIdx.y * kWarp + lane_id();
     const bool col_ok = c < k && active[c];
     double dot = 0.0;
-    // a strip whose 32 columns have all stopped does no work (uniform per warp)
-    if (__any_sync(0xffffffffu, col_ok)) {
-        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
-            const int64_t p0 = indptr[i], p1 = indptr[i + 1];
-            const double pi = col_ok ? p[i * (int64_t)k + c] : 0.0;
+    if (__any_sync(0xffffffffu, col_ok)) {  // a strip whose 32 columns have all stopped does no work
+        for (int64_t it = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); it < num_items; it += (int64_t)gridDim.x * kWarps) {
+            const int32_t i = items[it].row;
+            const int seg = items[it].seg;
+            const int64_t row0 = indptr[i], row1 = indptr[i + 1];
+            const int64_t p0 = row0 + (int64_t)seg * kSeg;
+            const int64_t p1 = min(p0 + kSeg, row1);
+            const bool single = row1 - row0 <= kSeg;
+            const double pi = (col_ok && single) ? p[i * (int64_t)k + c] : 0.0;
             const double dterm = __dmul_rn(diag[i], pi);
             double s = 0.0;
-            bool placed = false;
-            for (int64_t t = p0; t < p1; ++t) {
-                const int32_t j = __ldg(indices + t);
-                if (j == i) {                    // self loop: folded into diag (L_ii = deg - a_ii + reg)
-                    s = __dadd_rn(s, dterm);
-                    placed = true;
-                    continue;
+            bool placed = !single;                  // multi-segment rows: the diagonal is added by the combine kernel
+            for (int64_t t0 = p0; t0 < p1; t0 += 4) {
+                int32_t j[4];
+                double pj[4], a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = t0 + u < p1 ? __ldg(indices + t0 + u) : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pj[u] = (col_ok && j[u] >= 0) ? __ldg(p + (int64_t)j[u] * k + c) : 0.0;
+                    a[u] = (data && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
                 }
-                if (!placed && j > i) {
-                    s = __dadd_rn(s, dterm);
-                    placed = true;
-                }
-                if (col_ok) {
-                    const double pj = __ldg(p + (int64_t)j * k + c);
-                    s = data ? __dadd_rn(s, __dmul_rn(-__ldg(data + t), pj)) : __dsub_rn(s, pj);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j[u] < 0) break;
+                    if (j[u] == i) {                // self loop: folded into diag (L_ii = deg - a_ii + reg)
+                        if (!placed) { s = __dadd_rn(s, dterm); placed = true; }
+                        continue;
+                    }
+                    if (!placed && j[u] > i) { s = __dadd_rn(s, dterm); placed = true; }
+                    s = data ? __dadd_rn(s, __dmul_rn(-a[u], pj[u])) : __dsub_rn(s, pj[u]);
                 }
             }
             if (!placed) s = __dadd_rn(s, dterm);
             if (col_ok) {
+                if (single) {
+                    q[i * (int64_t)k + c] = s;
+                    dot = __dadd_rn(dot, __dmul_rn(pi, s));
+                } else if (seg == 0) {
+                    q[i * (int64_t)k + c] = s;
+                } else {   // extra segments of all rows are numbered consecutively: (items before row i) - i + seg - 1
+                    const int64_t slot = (i ? seg_incl[i - 1] : 0) - i + seg - 1;
+                    segpart[slot * k + c] = s;
+                }
+            }
+        }
+    }
+    block_column_partial(dot, c < k, c, k, partial);
+}
+
+// Rows longer than kSeg: q[i] = seg0 + diag*p_i + seg1 + seg2 + ...   and their share of p.q
+__global__ void __launch_bounds__(kThreads)
+spmm_combine_kernel(int64_t n, const int64_t* __restrict__ seg_incl, const int64_t* __restrict__ indptr,
+                    const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
+                    const double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
+    const int c = blockIdx.y * kWarp + lane_id();
+    const bool col_ok = c < k && active[c];
+    double dot = 0.0;
+    if (__any_sync(0xffffffffu, col_ok)) {
+        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
+            if (indptr[i + 1] - indptr[i] <= kSeg) continue;
+            const int64_t before = i ? seg_incl[i - 1] : 0;
+            const int64_t nseg = seg_incl[i] - before;
+            if (col_ok) {
+                const double pi = p[i * (int64_t)k + c];
+                double s = __dadd_rn(q[i * (int64_t)k + c], __dmul_rn(diag[i], pi));
+                const int64_t slot0 = before - i;
+                for (int64_t sg = 1; sg < nseg; ++sg) s = __dadd_rn(s, segpart[(slot0 + sg - 1) * k + c]);
                 q[i * (int64_t)k + c] = s;
                 dot = __dadd_rn(dot, __dmul_rn(pi, s));
             }
         }
     }
     block_column_partial(dot, c < k, c, k, partial);
+}
+
+__global__ void seg_count_kernel(int64_t n, const int64_t* __restrict__ indptr, int64_t* __restrict__ counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = indptr[i + 1] - indptr[i];
+        counts[i] = d <= kSeg ? 1 : (d + kSeg - 1) / kSeg;
+    }
+}
+
+__global__ void seg_fill_kernel(int64_t n, const int64_t* __restrict__ incl, SegItem* __restrict__ items) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t before = i ? incl[i - 1] : 0;
+        const int64_t c = incl[i] - before;
+        for (int64_t sg = 0; sg < c; ++sg) items[before + sg] = SegItem{(int32_t)i, (int32_t)sg};
+    }
 }
 
 __global__ void alpha_kernel(int k, int nblocks, const double* __restrict__ partial, CgColumns cg) {
@@ -249,6 +320,30 @@ __global__ void er_finalize_kernel(int64_t n, double* s) {
 
 std::mutex g_und_mutex;
 
+int ensure_segments(Graph* g, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_und_mutex);
+    if (g->seg_items || g->n == 0) return GSP_OK;
+    Scratch<int64_t> counts;
+    GSP_CUDA_TRY(counts.alloc(g->n, s));
+    int64_t* incl = nullptr;
+    GSP_CUDA_TRY(cudaMalloc(&incl, (size_t)g->n * sizeof(int64_t)));
+    seg_count_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, counts.ptr);
+    GSP_CHECK_LAUNCH();
+    if (int rc = inclusive_sum_i64(counts.ptr, incl, g->n, s)) { cudaFree(incl); return rc; }
+    int64_t total = 0;
+    GSP_CUDA_TRY(cudaMemcpyAsync(&total, incl + (g->n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    SegItem* items = nullptr;
+    GSP_CUDA_TRY(cudaMalloc(&items, (size_t)total * sizeof(SegItem)));
+    seg_fill_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, incl, items);
+    GSP_CHECK_LAUNCH();
+    GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    g->seg_items = items;
+    g->seg_incl = incl;
+    g->num_seg_items = total;
+    return GSP_OK;
+}
+
 int ensure_und_id(Graph* g, void* stream) {
     std::lock_guard<std::mutex> lock(g_und_mutex);
     if (g->und_id || g->nnz == 0) return GSP_OK;
@@ -283,6 +378,8 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     cudaStream_t s = as_stream(stream);
     const int64_t n = g->n;
     if (int rc = ensure_und_id(g, stream)) return rc;
+    if (int rc = ensure_segments(g, s)) return rc;
+    const int64_t extra_segments = g->num_seg_items - n;   // > 0 when some row is longer than kSeg
 
     const int strips = (k + kWarp - 1) / kWarp;
     // row blocks: enough CTAs for >= 8 per SM over all strips, at most one warp-row each
@@ -301,7 +398,9 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     GSP_CUDA_TRY(r.alloc(vec, s));
     GSP_CUDA_TRY(p.alloc(vec, s));
     GSP_CUDA_TRY(q.alloc(vec, s));
-    GSP_CUDA_TRY(partial.alloc((size_t)nb * k, s));
+    GSP_CUDA_TRY(partial.alloc((size_t)2 * nb * k, s));   // second half: the combine kernel's p.q partials
+    Scratch<double> segpart;
+    GSP_CUDA_TRY(segpart.alloc((size_t)(extra_segments > 0 ? extra_segments : 1) * k, s));
     GSP_CUDA_TRY(diag.alloc(n, s));
     GSP_CUDA_TRY(cols.alloc((size_t)5 * k, s));
     GSP_CUDA_TRY(flags.alloc((size_t)k + 1, s));
@@ -332,10 +431,16 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
         GSP_CHECK_LAUNCH();
         direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
         GSP_CHECK_LAUNCH();
-        spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(n, g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, cg.active,
-                                                   partial.ptr);
+        spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(reinterpret_cast<const SegItem*>(g->seg_items), g->num_seg_items, g->seg_incl,
+                                                   g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,
+                                                   cg.active, partial.ptr);
         GSP_CHECK_LAUNCH();
-        alpha_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg);
+        if (extra_segments > 0) {
+            spmm_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,
+                                                           cg.active, partial.ptr + (size_t)nb * k);
+            GSP_CHECK_LAUNCH();
+        }
+        alpha_kernel<<<col_blocks, 128, 0, s>>>(k, extra_segments > 0 ? 2 * nb : nb, partial.ptr, cg);
         GSP_CHECK_LAUNCH();
         update_kernel<<<grid2d, kThreads, 0, s>>>(n, k, p.ptr, q.ptr, x.ptr, r.ptr, cg, partial.ptr);
         GSP_CHECK_LAUNCH();

@@ -83,6 +83,9 @@ struct Graph {
     int32_t* tidx = nullptr;
     // lazily built
     int32_t* und_id = nullptr;   // [nnz]
+    void* seg_items = nullptr;   // row segments of the Laplacian SpMM (approx_er.cu)
+    int64_t* seg_incl = nullptr; // [n] inclusive prefix of segments per row
+    int64_t num_seg_items = 0;
     void* owner_items = nullptr; // work items of the owner-hashed intersection (intersect_owner.cu)
     int64_t num_owner_items = 0; // medium-class items (first in the array)
     int64_t num_hub_items = 0;   // hub-class items (after them)

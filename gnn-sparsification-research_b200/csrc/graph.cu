@@ -233,6 +233,8 @@ void free_graph(Graph* g) {
     cudaFree(g->tidx);
     cudaFree(g->und_id);
     cudaFree(g->owner_items);
+    cudaFree(g->seg_items);
+    cudaFree(g->seg_incl);
     delete g;
 }
 

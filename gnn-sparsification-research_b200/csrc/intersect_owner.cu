@@ -13,13 +13,15 @@
 //   level A  rows with 1 <= deg <= 64: one warp per owner, 128-slot table per warp, neighbours in registers
 //   level B  rows with deg > 64: CTA per (owner, neighbour chunk). Two size classes of the same kernel:
 //            64 < deg <= 1536: 256 threads, 4096 cuckoo slots, 512-neighbour chunks (~6 CTAs per SM);
-//            deg > 1536: 640 threads, two CTAs per SM, the owner row hashed in tiles of 6144 ids (16384 slots),
+//            deg > 1536: 768 threads, two CTAs per SM, the owner row hashed in tiles of 6144 ids (16384 slots),
 //            tiles visited in DESCENDING id order so Adamic-Adar keeps SciPy's accumulation order. Neighbour
 //            metadata is fetched once per item; each neighbour keeps a cursor into its row between tiles.
 //
 // An edge range [e_begin, e_end) (multi-GPU sharding) restricts the pairs to those with a directed position
 // inside the range; only in-range positions are written.
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -259,12 +261,12 @@ struct OwnerClass {
 // slots = both cuckoo tables together; a tile holds at most kTileLoad * slots owner ids (load factor 0.375)
 constexpr int kMediumMaxDegree = 1536;
 constexpr OwnerClass kMediumClass{4096, 512, 256};       // 16 KB tables + 16 KB state: ~6 CTAs / SM
-constexpr OwnerClass kHubClass{16384, 1024, 640};        // 64 KB tables + 32 KB state: 2 CTAs / SM (register-limited)
+constexpr OwnerClass kHubClass{16384, 1024, 768};        // 64 KB tables + 36 KB state: 2 CTAs / SM (40 regs x 1536 threads)
 __host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3; }
 
 __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ordered_sum) {
-    // slots | base(int64) | acc(double) | len | cursor | rev | cnt | per-warp hit queues (Adamic-Adar only)
-    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4) +
+    // slots | base(int64) | acc(double) | len | cursor | rev | cnt | top | pad | per-warp hit queues (Adamic-Adar only)
+    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) +
            (ordered_sum ? (size_t)(c.threads / kWarp) * kWarp * sizeof(double) : 0);
 }
 
@@ -305,6 +307,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
             for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                if (k > 0 && top + lane - k * kWarp < 0) break;   // whole group below the row start (warp-uniform)
                 const bool hit = cuckoo_contains(table, x[k]);
                 if (x[k] == o) rev = top - k * kWarp;
                 if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, x[k], node_w, queue, acc);
@@ -313,14 +316,15 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
         cursor = 0;
     } else {
         bool done = false;
+        int groups = 1;   // a tile usually holds a short piece of the row: probe one group before going four deep
         while (cursor > 0 && !done) {
             const int top = cursor - 1 - lane;
             int32_t x[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
+            for (int k = 0; k < 4; ++k) x[k] = (k < groups && top - k * kWarp >= 0) ? __ldg(row_w + top - k * kWarp) : INT_MIN;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (done) break;
+                if (done || k >= groups) break;
                 const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
                 const bool hit = in_tile && cuckoo_contains(table, x[k]);
                 if (in_tile && x[k] == o) rev = top - k * kWarp;
@@ -331,7 +335,8 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                     cursor = cursor - k * kWarp - __popc(inside);
                 }
             }
-            if (!done) cursor -= 4 * kWarp;
+            if (!done) cursor -= groups * kWarp;
+            groups = 4;
         }
         if (cursor < 0) cursor = 0;
     }
@@ -353,7 +358,8 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
     int32_t* rev_s = cur_s + cls.chunk;                               // offset of o inside row(w)
     int32_t* cnt_s = rev_s + cls.chunk;
-    double* queue = reinterpret_cast<double*>(cnt_s + cls.chunk) + (threadIdx.x >> 5) * kWarp;   // valid when kMode == 1
+    int32_t* top_s = cnt_s + cls.chunk;                               // largest unprocessed id of row(w) (INT_MIN: none)
+    double* queue = reinterpret_cast<double*>(top_s + 2 * cls.chunk) + (threadIdx.x >> 5) * kWarp;   // valid when kMode == 1
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
@@ -394,6 +400,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
             base_s[i] = b0;
             len_s[i] = skip ? -1 : d_w;
             cur_s[i] = d_w;
+            top_s[i] = (skip || d_w == 0) ? INT_MIN : __ldg(indices + b0 + d_w - 1);
             rev_s[i] = -1;
             cnt_s[i] = 0;
             acc_s[i] = 0.0;
@@ -429,9 +436,10 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                 if (i >= nb) break;
                 const int i_end = min(i + 4, nb);
                 for (; i < i_end; ++i) {
-                    const int d_w = len_s[i];
+                    // rows with nothing left in this tile's id range cost one shared-memory read (multi-tile owners chop
+                    // every neighbour row into pieces; most tiles miss most short rows)
+                    if (top_s[i] < lo_id) continue;
                     const int cursor = cur_s[i];
-                    if (d_w < 0 || cursor <= 0) continue;
                     int count = 0, rev = -1;
                     double acc = kMode == 1 ? acc_s[i] : 0.0;
                     const int32_t* row_w = indices + base_s[i];
@@ -441,7 +449,10 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                     if (lane == 0) {
                         if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
                         if (rev >= 0) rev_s[i] = rev;
-                        cur_s[i] = new_cursor;
+                        if (t > 0) {   // the lowest tile consumes the rest of the row: nothing to carry over
+                            cur_s[i] = new_cursor;
+                            top_s[i] = new_cursor > 0 ? __ldg(row_w + new_cursor - 1) : INT_MIN;
+                        }
                     }
                 }
             }
@@ -516,13 +527,26 @@ int ensure_items(Graph* g, cudaStream_t s) {
     return GSP_OK;
 }
 
+// Debug/tuning knobs: GSP_HUB_CLASS="slots,chunk,threads,ctas_per_sm" overrides the hub launch configuration
+// (the chunk must not exceed the value the work items were built with).
+OwnerClass hub_class_from_env(int& ctas_per_sm) {
+    OwnerClass c = kHubClass;
+    if (const char* env = getenv("GSP_HUB_CLASS")) {
+        int slots, chunk, threads, ctas;
+        if (sscanf(env, "%d,%d,%d,%d", &slots, &chunk, &threads, &ctas) == 4 && chunk == kHubClass.chunk) {
+            c = OwnerClass{slots, chunk, threads};
+            ctas_per_sm = ctas;
+        }
+    }
+    return c;
+}
+
 template <int kMode>
 int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, int ctas_per_sm, Graph* g, const RangeInfo& r,
                  const double* node_w, int32_t* inter, double* score, unsigned long long* counter, cudaStream_t s) {
     if (count <= 0) return GSP_OK;
     const size_t smem = owner_smem_bytes(cls, kMode == 1);
-    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)owner_smem_bytes(kHubClass, true)));
+    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
     cta_owner_kernel<kMode><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
@@ -553,7 +577,9 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 3 * sizeof(unsigned long long), s));
     const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
     // hubs first: their long work items should not land in the tail
-    if (int rc = launch_class<kMode>(kHubClass, items + g->num_owner_items, g->num_hub_items, 2, g, r, node_w, inter, score,
+    int hub_ctas = 2;
+    const OwnerClass hub = hub_class_from_env(hub_ctas);
+    if (int rc = launch_class<kMode>(hub, items + g->num_owner_items, g->num_hub_items, hub_ctas, g, r, node_w, inter, score,
                                      counters.ptr, s)) return rc;
     if (int rc = launch_class<kMode>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
                                      counters.ptr + 1, s)) return rc;

@@ -56,7 +56,7 @@ class DeviceGraph:
                 self._lib.gsp_graph_destroy(h)
             except Exception:
                 pass
-            self._handle = C.c_void_p()
+            self._handle = None
 
     # -- helpers ---------------------------------------------------------------------------------
     def _stream(self):

@@ -23,6 +23,23 @@ def make_sparsifier(ei, n, x=None, device="cpu"):
     return gsr_b200.GraphSparsifier(data, device)
 
 
+def hub_graph(n=30000, hub_deg=20500, extra=60000, seed=3):
+    """Two hubs whose rows span several 8192-id hash tiles, plus R-MAT edges among their neighbours."""
+    rng = np.random.default_rng(seed)
+    nb0 = rng.choice(np.arange(2, n), hub_deg, replace=False)
+    nb1 = rng.choice(np.arange(2, n), hub_deg // 2, replace=False)
+    base = rmat_graph(n, extra, 15, seed=seed)
+    lo = np.concatenate([np.zeros_like(nb0), np.ones_like(nb1), np.minimum(base[0], base[1]), [0]])
+    hi = np.concatenate([nb0, nb1, np.maximum(base[0], base[1]), [1]])
+    keys = np.unique(lo * n + hi)
+    lo, hi = keys // n, keys % n
+    keep = lo != hi
+    lo, hi = lo[keep], hi[keep]
+    row, col = np.concatenate([lo, hi]), np.concatenate([hi, lo])
+    order = np.lexsort((col, row))
+    return np.vstack([row[order], col[order]]), n
+
+
 # ----------------------------------------------------------------------------- golden fixtures
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_fixture(name):
@@ -206,7 +223,7 @@ def test_weighted_adjacency_approx_er_like_reference_karate_test():
 
 
 # ----------------------------------------------------------------------------- ApproxER
-@pytest.mark.parametrize("case", ["rmat", "chain_converged", "chain_capped"])
+@pytest.mark.parametrize("case", ["rmat", "hub_rows", "chain_converged", "chain_capped"])
 def test_approx_er_against_oracle(case):
     """Scores <= 1e-4 relative and >= 99.9 % kept-set agreement (north_star).
 
@@ -217,6 +234,9 @@ def test_approx_er_against_oracle(case):
         n = 3000
         ei = rmat_graph(n, 20000, 12, seed=77)
         k, iters_cap, rtol = 48, 500, 1e-4
+    elif case == "hub_rows":                      # rows longer than the SpMM's 512-neighbour segments
+        ei, n = hub_graph(n=4000, hub_deg=2500, extra=12000, seed=4)
+        k, iters_cap, rtol = 40, 500, 1e-4
     else:
         n = 1500
         ei = chain_with_shortcuts(n, 40, seed=5)
@@ -346,23 +366,6 @@ def test_properties_on_a_large_power_law_graph():
 
 
 # ----------------------------------------------------------------------------- intersection schedules
-def hub_graph(n=30000, hub_deg=20500, extra=60000, seed=3):
-    """Two hubs whose rows span several 8192-id hash tiles, plus R-MAT edges among their neighbours."""
-    rng = np.random.default_rng(seed)
-    nb0 = rng.choice(np.arange(2, n), hub_deg, replace=False)
-    nb1 = rng.choice(np.arange(2, n), hub_deg // 2, replace=False)
-    base = rmat_graph(n, extra, 15, seed=seed)
-    lo = np.concatenate([np.zeros_like(nb0), np.ones_like(nb1), np.minimum(base[0], base[1]), [0]])
-    hi = np.concatenate([nb0, nb1, np.maximum(base[0], base[1]), [1]])
-    keys = np.unique(lo * n + hi)
-    lo, hi = keys // n, keys % n
-    keep = lo != hi
-    lo, hi = lo[keep], hi[keep]
-    row, col = np.concatenate([lo, hi]), np.concatenate([hi, lo])
-    order = np.lexsort((col, row))
-    return np.vstack([row[order], col[order]]), n
-
-
 @pytest.mark.parametrize("schedule", ["owner", "general"])
 def test_hub_rows_and_both_intersection_schedules(schedule, monkeypatch):
     if schedule == "general":
