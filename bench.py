@@ -153,6 +153,58 @@ def workload_name(args) -> str:
             f"{args.dim}-d fp32 features; Jaccard/AA/FeatCos scoring + top-{int(RETENTION * 100)}% select + compaction")
 
 
+def run_approx_er(args, dev, rank, world, group):
+    """ApproxER-T sparsify (scores + top-50 % select + compaction) on the products-shaped R-MAT graph; projection columns
+    are split over the ranks and the per-edge partial sums all-reduced (NCCL). Device Philox projection (throughput
+    mode; parity mode feeds the reference's NumPy matrix, tests/test_gpu_parity.py)."""
+    from gsr_b200 import engine
+    from gsr_b200.metrics import _approx_er_on_graph
+    from gsr_b200.synthetic import SHAPES, rmat_graph_device
+
+    torch.cuda.empty_cache()
+    n4, e4, _, scale4, seed4 = SHAPES[args.er_shape]
+    ei4 = rmat_graph_device(n4, e4, scale4, seed4, dev)
+    g4 = engine.DeviceGraph(ei4, n4)
+    k = 64
+    _approx_er_on_graph(g4, k=8, max_cg_iters=3, projection="device", group=group)      # builds the lazy side structures
+    if world > 1:
+        torch.distributed.barrier(group)
+    torch.cuda.synchronize(dev)
+    t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t0.record()
+    scores, iters = _approx_er_on_graph(g4, k=k, max_cg_iters=500, cg_tol=1e-6, projection="device", group=group,
+                                        return_iters=True)
+    t1.record()
+    keep = int(e4 * RETENTION)
+    mask = engine.select_mask(scores, keep, False)
+    engine.compact_edges(ei4, mask, keep)
+    t2.record()
+    torch.cuda.synchronize(dev)
+    score_ms, total_ms = t0.elapsed_time(t1), t0.elapsed_time(t2)
+    tms = torch.tensor([score_ms, total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX, group=group)
+    it = iters.float()
+    k_loc = (k + world - 1) // world
+    iters_run = int(iters.max().item())
+    per_iter_ms = float(tms[0]) / max(iters_run, 1)
+    bytes_reuse = 4.0 * g4.nnz + 8.0 * k_loc * 10 * n4
+    bytes_noreuse = 4.0 * g4.nnz + 8.0 * k_loc * (g4.nnz + 9 * n4)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    return {"workload": f"{args.er_shape}-shaped R-MAT: {n4} nodes, {e4} directed edges; JLT k={k}, CG rtol 1e-6, <=500 iterations, reg 1e-6",
+            "score_ms": float(tms[0]), "sparsify_ms": float(tms[1]), "edges_per_s": e4 / (float(tms[1]) * 1e-3),
+            "cg_iterations": {"min": int(it.min()), "mean": float(it.mean()), "max": iters_run}, "columns_per_gpu": k_loc,
+            "ms_per_cg_iteration": per_iter_ms,
+            "roofline_per_iteration": {"alg_gb_perfect_reuse": bytes_reuse / 1e9, "alg_gb_no_reuse": bytes_noreuse / 1e9,
+                                       "frac_perfect_reuse": bytes_reuse / (per_iter_ms * 1e-3) / 1e9 / peak,
+                                       "frac_no_reuse": bytes_noreuse / (per_iter_ms * 1e-3) / 1e9 / peak},
+            "max_degree": g4.max_degree, "projection": "device Philox normals / sqrt(k)"}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +217,8 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-approx-er", action="store_true", help="skip the ApproxER sparsify timing (BASELINE config 4)")
+    ap.add_argument("--er-shape", default="products")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)   # the driver passes W; timing rules ask for >= 3 in reported runs
@@ -287,6 +341,20 @@ def main() -> None:
     ms_per_step = float(elapsed_ms) / args.steps
     value = len(METHODS) * e / (ms_per_step * 1e-3)
 
+    # graph statistics for the roofline accounting (rank 0; needs the graph, so before it is released below)
+    s2 = graph.sum_degree_sq
+    max_degree = graph.max_degree
+    sum_min = common = 0.0
+    if rank == 0:
+        indptr_t, indices_t, _, rows_t = graph.export(with_data=False, with_rows=True)
+        deg_t = indptr_t[1:] - indptr_t[:-1]
+        sum_min = float(torch.minimum(deg_t[rows_t.long()], deg_t[indices_t.long()]).sum()) / 2.0
+        del indptr_t, indices_t, rows_t, deg_t
+        _, inter_t = graph.jaccard(return_counts=True)
+        common = float(inter_t.sum(dtype=torch.int64)) / 2.0
+        del inter_t
+        torch.cuda.synchronize(dev)
+
     # ---- e2e through the reference-facing API, host inputs (rank-local replica; N>1 repeats it per rank) ----
     e2e = None
     if not args.no_e2e and world == 1:
@@ -314,6 +382,10 @@ def main() -> None:
                "d2h_bytes_per_step": int(d2h), "ms_per_step": sum(times) / len(times) * 1e3,
                "api": "data_host.to(cuda) -> GraphSparsifier(data, cuda) -> compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, return_mask=True) [host bool mask] for 3 metrics"}
 
+    # ---- ApproxER sparsify ms (BASELINE config 4: products-shaped graph, JLT k = 64, CG rtol 1e-6, <= 500 iterations) ----
+    approx_er = None
+    if not args.no_approx_er:
+        approx_er = run_approx_er(args, dev, rank, world, group)
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -325,19 +397,11 @@ def main() -> None:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); peak_src = "measured"
     except Exception:
         pass
-    s2 = graph.sum_degree_sq
     frac_edges = local / e
     # Algorithmic bytes (DESIGN.md "Roofline accounting"). The owner-hashed intersection streams, for every undirected
     # pair, only the SHORTER neighbour list: sum_pairs min(d_u, d_v) ids, plus the owner rows once (4E), neighbour
     # metadata (16E) and the fp64 output (8E); Adamic-Adar adds one 8-byte weight gather per common neighbour.
     # SURVEY 8d's formula (4*S2 + 20E: row(v) streamed once per directed edge) is reported beside it.
-    indptr_t, indices_t, _, rows_t = graph.export(with_data=False, with_rows=True)
-    deg_t = indptr_t[1:] - indptr_t[:-1]
-    sum_min = float(torch.minimum(deg_t[rows_t.long()], deg_t[indices_t.long()]).sum()) / 2.0
-    del indptr_t, indices_t, rows_t, deg_t
-    _, inter_t = graph.jaccard(return_counts=True)
-    common = float(inter_t.sum(dtype=torch.int64)) / 2.0
-    del inter_t
     alg_bytes = {
         "jaccard": (4.0 * sum_min + 28.0 * e) * frac_edges,
         "adamic_adar": (4.0 * sum_min + 28.0 * e + 8.0 * common) * frac_edges,
@@ -377,10 +441,10 @@ def main() -> None:
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
-        "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": graph.max_degree,
+        "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": max_degree,
                    "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
                    "parallelism": f"x{world}: owner-sharded Jaccard/AA + reduce-scatter, edge-sliced FeatCos/select, CSR+features replicated"},
-        "per_method": per_kernel, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "per_method": per_kernel, "approx_er": approx_er, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "gsp_degree_product": (_INT, [_P, _I64, _I64, _P, _P]),
     "gsp_featcos_normalize_f32": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
     "gsp_featcos_f32": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),
+    "gsp_featcos_normalize_f32_packed": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
+    "gsp_featcos_f32_packed": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),
     "gsp_featcos_normalize_f64": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
     "gsp_featcos_f64": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),
     "gsp_approx_er_partial": (_INT, [_P, _P, _I64, _I32, _I32, _F64, _F64, _I64, _I64, _P, _P, _P]),

@@ -28,6 +28,15 @@ from . import _lib
 from .engine import DeviceGraph, compact_edges, degree_aware_guarantee, select_mask
 
 
+def _to_host(t: torch.Tensor) -> torch.Tensor:
+    """Device -> host through page-locked memory (torch's caching host allocator recycles the blocks), so the
+    fp64 score vectors and masks the reference API returns on the host move at PCIe speed."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
+
+
 class GraphSparsifier:
     """Engine for graph sparsification via edge metric thresholding (reference core.py:24)."""
 
@@ -183,7 +192,7 @@ class GraphSparsifier:
         """Edge scores as float64 ndarray in canonical CSR order (reference core.py:140-191)."""
         key = self._normalize_metric_name(metric)
         if key not in self._score_cache:
-            self._score_cache[key] = self._device_scores(key).cpu().numpy()
+            self._score_cache[key] = _to_host(self._device_scores(key)).numpy()
         return self._score_cache[key]
 
     # ------------------------------------------------------------------------------ selection
@@ -203,7 +212,7 @@ class GraphSparsifier:
         sparse_data = self.data.clone()
         sparse_data.edge_index = kept.to(self.device)
         if return_mask:
-            return sparse_data, mask_dev.cpu().bool()
+            return sparse_data, _to_host(mask_dev.view(torch.bool))   # 0/1 bytes reinterpreted, no conversion pass
         return sparse_data
 
     def _threshold_mask(self, scores: torch.Tensor, num_keep: int, keep_lowest: bool) -> Tuple[torch.Tensor, int]:
@@ -247,7 +256,7 @@ class GraphSparsifier:
         ei, w, _ = compact_edges(self._ei_dev, mask, kept, scores=scores, with_weights=True, invert_weights=keep_lowest)
         sparse_data = self.data.clone()
         sparse_data.edge_index = ei.to(self.device)
-        return sparse_data, w.to(self.device), mask.cpu().bool()
+        return sparse_data, w.to(self.device), _to_host(mask.view(torch.bool))
 
     def sparsify_metric_backbone(self, metric: str, epsilon: float = 1e-9):
         """Metric-backbone sparsification (reference core.py:251-279) — APSP based, outside the B200 hot path."""

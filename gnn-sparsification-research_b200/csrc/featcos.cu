@@ -133,6 +133,78 @@ featcos_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ rows,
     }
 }
 
+// ---- packed fp32 fast path (dim % 32 == 0, dim <= 128: one pairwise leaf) -----------------------------------------
+// The normalised row is stored accumulator-major: packed[q*32 + j*4 + k] = xhat[j + 8*(4q + k)], i.e. the four
+// consecutive chain elements (4q .. 4q+3) of NumPy accumulator j sit in one float4 and the eight lanes of an edge
+// group read 128 contiguous bytes per load. Same arithmetic, same association order, a quarter of the load
+// instructions (the scalar kernel is LSU-issue bound, not HBM bound).
+__global__ void __launch_bounds__(kThreads)
+normalize_packed_kernel(int64_t n, int dim, const float* __restrict__ x, int64_t ld, float* __restrict__ packed, int64_t ld_out) {
+    using A = Arith<float>;
+    const int j = threadIdx.x & (kGroup - 1);
+    const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
+    const int64_t num_groups = (int64_t)gridDim.x * blockDim.x / kGroup;
+    const int64_t rounds = (n + num_groups - 1) / num_groups;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t node = it * num_groups + group;
+        const bool live = node < n;
+        const float* row = x + (live ? node : 0) * ld;
+        float ss = leaf_sum<float>([&](int i) { float v = row[i]; return A::mul(v, v); }, dim, j);
+        float nrm = A::sqrt(ss);
+        nrm = nrm < A::floor_norm() ? A::floor_norm() : nrm;
+        if (live) {
+            float* out = packed + node * ld_out;
+            for (int i = j; i < dim; i += kGroup) {
+                const int m = i >> 3;                       // position in accumulator j's chain
+                out[(m >> 2) * 32 + j * 4 + (m & 3)] = A::div(row[i], nrm);
+            }
+        }
+    }
+}
+
+template <int kQuads>   // kQuads = dim / 32 float4 loads per lane and row
+__global__ void __launch_bounds__(kThreads)
+featcos_packed_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ rows, const int32_t* __restrict__ indices,
+                      const float* __restrict__ packed, int64_t ld, double* __restrict__ out) {
+    using A = Arith<float>;
+    const int j = threadIdx.x & (kGroup - 1);
+    const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
+    const int64_t num_groups = (int64_t)gridDim.x * blockDim.x / kGroup;
+    const int64_t count = e_end - e_begin;
+    const int64_t rounds = (count + num_groups - 1) / num_groups;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t k = it * num_groups + group;
+        const bool live = k < count;
+        const int64_t e = e_begin + (live ? k : 0);
+        const float4* pu = reinterpret_cast<const float4*>(packed + (int64_t)__ldg(rows + e) * ld) + j;
+        const float4* pv = reinterpret_cast<const float4*>(packed + (int64_t)__ldg(indices + e) * ld) + j;
+        float4 a[kQuads], b[kQuads];
+#pragma unroll
+        for (int q = 0; q < kQuads; ++q) {
+            a[q] = __ldg(pu + q * 8);
+            b[q] = __ldg(pv + q * 8);
+        }
+        float r = A::mul(a[0].x, b[0].x);                   // r[j] = a[j]
+        r = A::add(r, A::mul(a[0].y, b[0].y));
+        r = A::add(r, A::mul(a[0].z, b[0].z));
+        r = A::add(r, A::mul(a[0].w, b[0].w));
+#pragma unroll
+        for (int q = 1; q < kQuads; ++q) {
+            r = A::add(r, A::mul(a[q].x, b[q].x));
+            r = A::add(r, A::mul(a[q].y, b[q].y));
+            r = A::add(r, A::mul(a[q].z, b[q].z));
+            r = A::add(r, A::mul(a[q].w, b[q].w));
+        }
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        r = r < 0.0f ? 0.0f : r;
+        if (live && j == 0) out[k] = (double)r;
+    }
+}
+
+inline bool packed_ok(int32_t dim, int64_t ld) { return dim >= 32 && dim <= 128 && dim % 32 == 0 && ld % 4 == 0; }
+
 template <typename T>
 int normalize(int64_t n, int32_t dim, const T* x, int64_t ld, T* xhat, int64_t ld_out, cudaStream_t s) {
     GSP_REQUIRE(n >= 0 && dim >= 0, "negative size");
@@ -179,4 +251,40 @@ GSP_API int gsp_featcos_f32(const gsp_graph* g, const float* d_xhat, int32_t dim
 GSP_API int gsp_featcos_f64(const gsp_graph* g, const double* d_xhat, int32_t dim, int64_t ld, int64_t e_begin,
                             int64_t e_end, double* d_score, void* stream) {
     return featcos<double>(reinterpret_cast<const Graph*>(g), d_xhat, dim, ld, e_begin, e_end, d_score, as_stream(stream));
+}
+
+// Packed-layout variants (fp32, dim in {32, 64, 96, 128}): d_packed is an opaque accumulator-major copy of the
+// normalised features, valid only as input of gsp_featcos_f32_packed. Results are bit-identical to the plain pair.
+GSP_API int gsp_featcos_normalize_f32_packed(int64_t num_nodes, int32_t dim, const float* d_x, int64_t ld, float* d_packed,
+                                             int64_t ld_out, void* stream) {
+    GSP_REQUIRE(num_nodes >= 0, "negative size");
+    GSP_REQUIRE(packed_ok(dim, ld_out) && ld >= dim && ld_out >= dim, "packed layout needs dim in {32,64,96,128} and ld_out % 4 == 0");
+    if (num_nodes == 0) return GSP_OK;
+    GSP_REQUIRE(d_x && d_packed, "NULL feature pointer");
+    GSP_REQUIRE((reinterpret_cast<uintptr_t>(d_packed) & 15) == 0, "d_packed must be 16-byte aligned");
+    normalize_packed_kernel<<<grid_for(num_nodes * kGroup, kThreads, 8), kThreads, 0, as_stream(stream)>>>(
+        num_nodes, dim, d_x, ld, d_packed, ld_out);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_featcos_f32_packed(const gsp_graph* gg, const float* d_packed, int32_t dim, int64_t ld, int64_t e_begin,
+                                   int64_t e_end, double* d_score, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    GSP_REQUIRE(g != nullptr, "graph is NULL");
+    GSP_REQUIRE(e_begin >= 0 && e_begin <= e_end && e_end <= g->nnz, "edge range outside [0, nnz]");
+    GSP_REQUIRE(packed_ok(dim, ld) && ld >= dim, "packed layout needs dim in {32,64,96,128} and ld % 4 == 0");
+    if (e_begin == e_end) return GSP_OK;
+    GSP_REQUIRE(d_packed && d_score, "NULL argument");
+    GSP_REQUIRE((reinterpret_cast<uintptr_t>(d_packed) & 15) == 0, "d_packed must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    const int grid = grid_for((e_end - e_begin) * kGroup, kThreads, 8);
+    switch (dim / 32) {
+        case 1: featcos_packed_kernel<1><<<grid, kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, d_packed, ld, d_score); break;
+        case 2: featcos_packed_kernel<2><<<grid, kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, d_packed, ld, d_score); break;
+        case 3: featcos_packed_kernel<3><<<grid, kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, d_packed, ld, d_score); break;
+        default: featcos_packed_kernel<4><<<grid, kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, d_packed, ld, d_score); break;
+    }
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
 }

@@ -146,23 +146,36 @@ class DeviceGraph:
             check(self._lib.gsp_degree_product(self._handle, b, e, ptr(score), self._stream()))
         return score
 
-    def normalize_features(self, x: torch.Tensor) -> torch.Tensor:
-        """Row-normalised features in the dtype of `x` (fp32 or fp64), reference metrics.py:344-346."""
+    def normalize_features(self, x: torch.Tensor, packed: Optional[bool] = None) -> torch.Tensor:
+        """Row-normalised features in the dtype of `x` (fp32 or fp64), reference metrics.py:344-346.
+
+        fp32 features with dim in {32, 64, 96, 128} are stored in the accumulator-major packed layout of
+        `gsp_featcos_f32_packed` (the returned tensor carries `_gsp_packed = True`; it is only meaningful as input of
+        `feature_cosine`). `packed=False` forces the plain layout."""
         if x.dim() != 2 or x.size(0) != self.num_nodes:
             raise ValueError("features must have shape [num_nodes, d]")
         if x.dtype not in (torch.float32, torch.float64):
             x = x.to(torch.float64)  # NumPy promotes integer features to float64 in linalg.norm / divide
         x = x.to(self.device).contiguous()
         xhat = torch.empty_like(x)
-        fn = self._lib.gsp_featcos_normalize_f32 if x.dtype == torch.float32 else self._lib.gsp_featcos_normalize_f64
+        dim = x.size(1)
+        use_packed = x.dtype == torch.float32 and dim in (32, 64, 96, 128) and packed is not False
+        if use_packed:
+            fn = self._lib.gsp_featcos_normalize_f32_packed
+        else:
+            fn = self._lib.gsp_featcos_normalize_f32 if x.dtype == torch.float32 else self._lib.gsp_featcos_normalize_f64
         with torch.cuda.device(self.device):
-            check(fn(x.size(0), x.size(1), ptr(x), x.size(1), ptr(xhat), x.size(1), self._stream()))
+            check(fn(x.size(0), dim, ptr(x), dim, ptr(xhat), dim, self._stream()))
+        xhat._gsp_packed = use_packed
         return xhat
 
     def feature_cosine(self, xhat: torch.Tensor, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         score = self._empty(e - b, torch.float64) if out is None else out
-        fn = self._lib.gsp_featcos_f32 if xhat.dtype == torch.float32 else self._lib.gsp_featcos_f64
+        if getattr(xhat, "_gsp_packed", False):
+            fn = self._lib.gsp_featcos_f32_packed
+        else:
+            fn = self._lib.gsp_featcos_f32 if xhat.dtype == torch.float32 else self._lib.gsp_featcos_f64
         with torch.cuda.device(self.device):
             check(fn(self._handle, ptr(xhat), xhat.size(1), xhat.stride(0), b, e, ptr(score), self._stream()))
         return score

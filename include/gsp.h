@@ -122,6 +122,13 @@ int gsp_featcos_normalize_f32(int64_t num_nodes, int32_t dim, const float* d_x, 
                               int64_t ld_out, void* stream);
 int gsp_featcos_f32(const gsp_graph* g, const float* d_xhat, int32_t dim, int64_t ld, int64_t e_begin, int64_t e_end,
                     double* d_score, void* stream);
+/* Packed fast path for fp32 features with dim in {32, 64, 96, 128}: d_packed is an opaque, accumulator-major copy of
+ * the normalised rows (16-byte aligned, ld % 4 == 0) that only gsp_featcos_f32_packed reads — 128-bit loads, the same
+ * arithmetic and association order, bit-identical scores. */
+int gsp_featcos_normalize_f32_packed(int64_t num_nodes, int32_t dim, const float* d_x, int64_t ld, float* d_packed,
+                                     int64_t ld_out, void* stream);
+int gsp_featcos_f32_packed(const gsp_graph* g, const float* d_packed, int32_t dim, int64_t ld, int64_t e_begin,
+                           int64_t e_end, double* d_score, void* stream);
 int gsp_featcos_normalize_f64(int64_t num_nodes, int32_t dim, const double* d_x, int64_t ld, double* d_xhat,
                               int64_t ld_out, void* stream);
 int gsp_featcos_f64(const gsp_graph* g, const double* d_xhat, int32_t dim, int64_t ld, int64_t e_begin,

@@ -166,7 +166,7 @@ def test_arxiv_shape_degree_aware_and_sampled():
     assert bits_equal(sp.compute_scores("feature_cosine"), co.calculate_feature_cosine_scores(csr, x))
 
 
-@pytest.mark.parametrize("dim", [1, 5, 7, 8, 9, 31, 64, 100, 127, 128, 129, 130, 255, 256, 257, 300, 513, 1433])
+@pytest.mark.parametrize("dim", [1, 5, 7, 8, 9, 31, 32, 64, 96, 100, 127, 128, 129, 130, 255, 256, 257, 300, 513, 1433])
 def test_feature_cosine_summation_tree_all_dims(dim):
     n = 200
     ei = rmat_graph(n, 1200, 8, seed=dim)
@@ -177,6 +177,11 @@ def test_feature_cosine_summation_tree_all_dims(dim):
     assert bits_equal(sp.compute_scores("feature_cosine"), co.calculate_feature_cosine_scores(csr, x))
     sp64 = make_sparsifier(ei, n, x.astype(np.float64))
     assert bits_equal(sp64.compute_scores("feature_cosine"), co.calculate_feature_cosine_scores(csr, x.astype(np.float64)))
+    if dim in (32, 64, 96, 128):   # packed (float4) and plain layouts give the same bits
+        g = sp.graph
+        plain = g.feature_cosine(g.normalize_features(torch.from_numpy(x), packed=False))
+        assert getattr(sp._xhat, "_gsp_packed", False)
+        assert bits_equal(plain.cpu().numpy(), sp.compute_scores("feature_cosine"))
 
 
 def test_feature_cosine_requires_features():
