@@ -257,7 +257,6 @@ def main() -> None:
     node_range = sharding.owner_node_ranges(graph, world)[rank]
     full_scratch = torch.empty(slice_len * world, dtype=torch.float64, device=dev) if world > 1 else None
     num_keep = int(e * RETENTION)
-    deg_table = None
 
     scores = torch.empty(slice_len if world > 1 else local, dtype=torch.float64, device=dev)
     mask = torch.empty(local, dtype=torch.uint8, device=dev)
@@ -269,12 +268,8 @@ def main() -> None:
     kernel_ms["select+compact"] = 0.0
 
     def aa_weights():
-        # constant table of node weights per distinct degree (NumPy expression), gathered on device
-        nonlocal deg_table
-        if deg_table is None:
-            t = np.arange(graph.max_degree + 1, dtype=np.float64)
-            deg_table = torch.from_numpy(1.0 / np.sqrt(np.maximum(np.log(t + 1), 1e-10))).to(dev)
-        return deg_table[graph.degrees().long()]
+        # per-degree constant table (NumPy expression, built once per graph) gathered per node on the device
+        return graph.aa_node_weights_numpy()
 
     def step(record: bool):
         for m in METHODS:

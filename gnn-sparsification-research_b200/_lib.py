@@ -51,6 +51,7 @@ PROTOTYPES = {
     "gsp_jaccard": (_INT, [_P, _I64, _I64, _P, _P, _P]),
     "gsp_adamic_adar": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "gsp_aa_node_weights": (_INT, [_P, _P, _P]),
+    "gsp_aa_node_weights_from_table": (_INT, [_P, _P, _I64, _P, _P]),
     "gsp_jaccard_owned": (_INT, [_P, _I64, _I64, _P, _P, _P]),
     "gsp_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "gsp_owner_costs": (_INT, [_P, _P, _P]),

@@ -174,11 +174,7 @@ class GraphSparsifier:
         reference; "device" uses CUDA's log (<= 1 ulp apart, scores within 1e-6)."""
         if self.aa_weights != "numpy":
             return None
-        g = self.graph
-        table = np.arange(g.max_degree + 1, dtype=np.float64)
-        table = 1.0 / np.sqrt(np.maximum(np.log(table + 1), 1e-10))
-        table_dev = torch.from_numpy(table).to(g.device)
-        return table_dev[g.degrees().long()]
+        return self.graph.aa_node_weights_numpy()
 
     def _approx_effective_resistance(self) -> torch.Tensor:
         from .metrics import _approx_er_on_graph

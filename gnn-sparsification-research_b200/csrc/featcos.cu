@@ -138,8 +138,9 @@ featcos_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ rows,
 // consecutive chain elements (4q .. 4q+3) of NumPy accumulator j sit in one float4 and the eight lanes of an edge
 // group read 128 contiguous bytes per load. Same arithmetic, same association order, a quarter of the load
 // instructions (the scalar kernel is LSU-issue bound, not HBM bound).
+template <int kQuads>
 __global__ void __launch_bounds__(kThreads)
-normalize_packed_kernel(int64_t n, int dim, const float* __restrict__ x, int64_t ld, float* __restrict__ packed, int64_t ld_out) {
+normalize_packed_kernel(int64_t n, const float* __restrict__ x, int64_t ld, float* __restrict__ packed, int64_t ld_out) {
     using A = Arith<float>;
     const int j = threadIdx.x & (kGroup - 1);
     const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
@@ -149,15 +150,23 @@ normalize_packed_kernel(int64_t n, int dim, const float* __restrict__ x, int64_t
         const int64_t node = it * num_groups + group;
         const bool live = node < n;
         const float* row = x + (live ? node : 0) * ld;
-        float ss = leaf_sum<float>([&](int i) { float v = row[i]; return A::mul(v, v); }, dim, j);
-        float nrm = A::sqrt(ss);
+        float v[4 * kQuads];                                   // accumulator j's chain: elements j, j+8, j+16, ...
+#pragma unroll
+        for (int m = 0; m < 4 * kQuads; ++m) v[m] = __ldg(row + j + 8 * m);
+        float r = A::mul(v[0], v[0]);                          // the leaf's sum of squares, NumPy's order
+#pragma unroll
+        for (int m = 1; m < 4 * kQuads; ++m) r = A::add(r, A::mul(v[m], v[m]));
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = A::add(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        float nrm = A::sqrt(r);
         nrm = nrm < A::floor_norm() ? A::floor_norm() : nrm;
         if (live) {
-            float* out = packed + node * ld_out;
-            for (int i = j; i < dim; i += kGroup) {
-                const int m = i >> 3;                       // position in accumulator j's chain
-                out[(m >> 2) * 32 + j * 4 + (m & 3)] = A::div(row[i], nrm);
-            }
+            float4* out = reinterpret_cast<float4*>(packed + node * ld_out) + j;
+#pragma unroll
+            for (int q = 0; q < kQuads; ++q)
+                out[q * 8] = make_float4(A::div(v[4 * q], nrm), A::div(v[4 * q + 1], nrm), A::div(v[4 * q + 2], nrm),
+                                         A::div(v[4 * q + 3], nrm));
         }
     }
 }
@@ -262,8 +271,14 @@ GSP_API int gsp_featcos_normalize_f32_packed(int64_t num_nodes, int32_t dim, con
     if (num_nodes == 0) return GSP_OK;
     GSP_REQUIRE(d_x && d_packed, "NULL feature pointer");
     GSP_REQUIRE((reinterpret_cast<uintptr_t>(d_packed) & 15) == 0, "d_packed must be 16-byte aligned");
-    normalize_packed_kernel<<<grid_for(num_nodes * kGroup, kThreads, 8), kThreads, 0, as_stream(stream)>>>(
-        num_nodes, dim, d_x, ld, d_packed, ld_out);
+    const int grid = grid_for(num_nodes * kGroup, kThreads, 8);
+    cudaStream_t s = as_stream(stream);
+    switch (dim / 32) {
+        case 1: normalize_packed_kernel<1><<<grid, kThreads, 0, s>>>(num_nodes, d_x, ld, d_packed, ld_out); break;
+        case 2: normalize_packed_kernel<2><<<grid, kThreads, 0, s>>>(num_nodes, d_x, ld, d_packed, ld_out); break;
+        case 3: normalize_packed_kernel<3><<<grid, kThreads, 0, s>>>(num_nodes, d_x, ld, d_packed, ld_out); break;
+        default: normalize_packed_kernel<4><<<grid, kThreads, 0, s>>>(num_nodes, d_x, ld, d_packed, ld_out); break;
+    }
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }

@@ -125,6 +125,14 @@ __global__ void aa_weights_kernel(int64_t n, const int64_t* __restrict__ indptr,
     }
 }
 
+__global__ void aa_weights_table_kernel(int64_t n, const int64_t* __restrict__ indptr, const double* __restrict__ table,
+                                        int64_t table_len, double* __restrict__ w) {
+    for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t d = indptr[u + 1] - indptr[u];
+        w[u] = table[d < table_len ? d : table_len - 1];
+    }
+}
+
 __global__ void weighted_degree_kernel(int64_t n, const int64_t* __restrict__ indptr, const double* __restrict__ data,
                                        double* __restrict__ deg) {
     for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n; u += (int64_t)gridDim.x * blockDim.x) {
@@ -200,6 +208,17 @@ GSP_API int gsp_aa_node_weights(const gsp_graph* gg, double* d_node_w, void* str
     const Graph* g = reinterpret_cast<const Graph*>(gg);
     if (g->n == 0) return GSP_OK;
     aa_weights_kernel<<<grid_for(g->n, 256), 256, 0, as_stream(stream)>>>(g->n, g->indptr, d_node_w);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_aa_node_weights_from_table(const gsp_graph* gg, const double* d_table, int64_t table_len, double* d_node_w,
+                                           void* stream) {
+    GSP_REQUIRE(gg && d_table && d_node_w, "NULL argument");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    GSP_REQUIRE(table_len > g->max_degree, "table must have max_degree + 1 entries");
+    if (g->n == 0) return GSP_OK;
+    aa_weights_table_kernel<<<grid_for(g->n, 256), 256, 0, as_stream(stream)>>>(g->n, g->indptr, d_table, table_len, d_node_w);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }

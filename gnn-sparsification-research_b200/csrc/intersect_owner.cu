@@ -279,14 +279,10 @@ __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ord
 // descending-id order, then every lane replays the queue (broadcast loads) with the sequential fp64 adds the
 // reference's SpGEMM performs. ~3 issue slots per hit instead of ~8 for a ballot/shuffle loop.
 template <int kMode>
-__device__ __forceinline__ void accumulate_hits(bool hit, int32_t x, const double* __restrict__ node_w, double* queue,
-                                                double& acc) {
+__device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queue, double& acc) {
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
     if (hits == 0) return;
-    if (hit) {
-        const double w = __ldg(node_w + x);
-        queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
-    }
+    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
     __syncwarp();
     const int n = __popc(hits);
 #pragma unroll 4
@@ -305,12 +301,27 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
             int32_t x[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
+            if (kMode == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (k > 0 && top + lane - k * kWarp < 0) break;   // whole group below the row start (warp-uniform)
-                const bool hit = cuckoo_contains(table, x[k]);
-                if (x[k] == o) rev = top - k * kWarp;
-                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, x[k], node_w, queue, acc);
+                for (int k = 0; k < 4; ++k) {
+                    if (k > 0 && top + lane - k * kWarp < 0) break;   // whole group below the row start (warp-uniform)
+                    c += cuckoo_contains(table, x[k]);
+                    if (x[k] == o) rev = top - k * kWarp;
+                }
+            } else {
+                // probe all four groups, then issue all weight gathers, then accumulate in order: the gather latency
+                // of a round is paid once instead of once per group
+                bool hit[4];
+                double w[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    hit[k] = cuckoo_contains(table, x[k]);
+                    if (x[k] == o) rev = top - k * kWarp;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accumulate_hits<kMode>(hit[k], w[k], queue, acc);
             }
         }
         cursor = 0;
@@ -328,7 +339,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
                 const bool hit = in_tile && cuckoo_contains(table, x[k]);
                 if (in_tile && x[k] == o) rev = top - k * kWarp;
-                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, x[k], node_w, queue, acc);
+                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, hit ? __ldg(node_w + x[k]) : 0.0, queue, acc);
                 const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
                 if (inside != 0xffffffffu) {           // ran off the tile (or the row): stop after this group
                     done = true;

@@ -59,29 +59,38 @@ histogram_kernel(const double* __restrict__ scores, int64_t count, const uint8_t
     const uint64_t prefix = st->prefix;
     const int hi_shift = shift + bits;  // bits above the current digit must match the prefix
     const unsigned int digit_mask = (1u << bits) - 1u;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t base = blockIdx.x * (int64_t)kThreads; base < count; base += stride) {
-        const int64_t i = base + threadIdx.x;
-        bool live = i < count;
-        unsigned int digit = 0;
-        if (live) {
-            if (exclude && exclude[i]) live = false;
-            else {
-                uint64_t k = select_key(scores[i], keep_lowest);
+    constexpr int kUnroll = 4;   // four independent 8-byte loads in flight per thread (the pass is latency bound otherwise)
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads * kUnroll; base < count; base += stride) {
+        double v[kUnroll];
+        uint8_t ex[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            v[u] = i < count ? scores[i] : 0.0;
+            ex[u] = (exclude && i < count) ? exclude[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t i = base + u * kThreads + threadIdx.x;
+            bool live = i < count && !ex[u];
+            unsigned int digit = 0;
+            if (live) {
+                uint64_t k = select_key(v[u], keep_lowest);
                 if (hi_shift < 64 && (k >> hi_shift) != (prefix >> hi_shift)) live = false;
                 digit = (unsigned int)(k >> shift) & digit_mask;
             }
-        }
-        // heavy tie classes (e.g. Jaccard's zeros) put whole warps on one bin: one atomic for the warp
-        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-        if (live_mask == 0) continue;
-        const int leader = __ffs(live_mask) - 1;
-        const unsigned int lead_digit = __shfl_sync(0xffffffffu, digit, leader);
-        const unsigned same = __ballot_sync(0xffffffffu, live && digit == lead_digit);
-        if (same == live_mask) {
-            if ((threadIdx.x & 31) == leader) atomicAdd(&sh[lead_digit], (unsigned int)__popc(live_mask));
-        } else if (live) {
-            atomicAdd(&sh[digit], 1u);
+            // heavy tie classes (e.g. Jaccard's zeros) put whole warps on one bin: one atomic for the warp
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            if (live_mask == 0) continue;
+            const int leader = __ffs(live_mask) - 1;
+            const unsigned int lead_digit = __shfl_sync(0xffffffffu, digit, leader);
+            const unsigned same = __ballot_sync(0xffffffffu, live && digit == lead_digit);
+            if (same == live_mask) {
+                if ((threadIdx.x & 31) == leader) atomicAdd(&sh[lead_digit], (unsigned int)__popc(live_mask));
+            } else if (live) {
+                atomicAdd(&sh[digit], 1u);
+            }
         }
     }
     __syncthreads();
@@ -138,9 +147,18 @@ count_ties_kernel(const double* __restrict__ scores, int64_t count, const uint8_
     const int64_t chunk = chunk_size(count, gridDim.x);
     const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
     unsigned long long c = 0;
-    if (!st->empty)
-        for (int64_t i = lo + threadIdx.x; i < hi; i += kThreads)
-            c += !(exclude && exclude[i]) && select_key(scores[i], keep_lowest) == t;
+    if (!st->empty) {
+        for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * kThreads) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = i0 + u * kThreads < hi ? scores[i0 + u * kThreads] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * kThreads;
+                c += i < hi && !(exclude && exclude[i]) && select_key(v[u], keep_lowest) == t;
+            }
+        }
+    }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh, c);
     __syncthreads();
@@ -400,7 +418,7 @@ GSP_API int gsp_select_histogram(const double* d_scores, int64_t count, const ui
     cudaStream_t s = as_stream(stream);
     GSP_CUDA_TRY(cudaMemsetAsync(d_hist, 0, kBins * sizeof(uint64_t), s));
     if (count == 0) return GSP_OK;
-    histogram_kernel<<<grid_for(count, 4 * kThreads, 8), kThreads, 0, s>>>(
+    histogram_kernel<<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(
         d_scores, count, d_exclude, reinterpret_cast<const SelectState*>(d_state), pass,
         reinterpret_cast<unsigned long long*>(d_hist));
     GSP_CHECK_LAUNCH();

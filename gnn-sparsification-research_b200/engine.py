@@ -109,6 +109,20 @@ class DeviceGraph:
             check(self._lib.gsp_aa_node_weights(self._handle, ptr(w), self._stream()))
         return w
 
+    def aa_node_weights_numpy(self) -> torch.Tensor:
+        """Node weights with NumPy's bits: the reference expression (metrics.py:104-108) evaluated once per distinct
+        degree value on the host (a table of max_degree + 1 constants), gathered per node on the device."""
+        import numpy as np
+
+        if getattr(self, "_aa_table", None) is None:
+            t = np.arange(self.max_degree + 1, dtype=np.float64)
+            self._aa_table = torch.from_numpy(1.0 / np.sqrt(np.maximum(np.log(t + 1), 1e-10))).to(self.device)
+        w = self._empty(self.num_nodes, torch.float64)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_aa_node_weights_from_table(self._handle, ptr(self._aa_table), self._aa_table.numel(), ptr(w),
+                                                           self._stream()))
+        return w
+
     def adamic_adar(self, node_weights: Optional[torch.Tensor] = None, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         if node_weights is not None:

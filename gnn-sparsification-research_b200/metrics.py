@@ -37,9 +37,7 @@ def graph_from_scipy(adj, device=None) -> DeviceGraph:
 
 def _numpy_aa_weights(g: DeviceGraph) -> torch.Tensor:
     # reference metrics.py:104-108 evaluated once per distinct degree (libm-defined constants), gathered on device
-    table = np.arange(g.max_degree + 1, dtype=np.float64)
-    table = 1.0 / np.sqrt(np.maximum(np.log(table + 1), 1e-10))
-    return torch.from_numpy(table).to(g.device)[g.degrees().long()]
+    return g.aa_node_weights_numpy()
 
 
 def calculate_jaccard_scores(adj) -> np.ndarray:

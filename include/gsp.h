@@ -97,6 +97,10 @@ int gsp_jaccard(const gsp_graph* g, int64_t e_begin, int64_t e_end, int32_t* d_i
 int gsp_adamic_adar(const gsp_graph* g, const double* d_node_w, int64_t e_begin, int64_t e_end, double* d_score,
                     void* stream);
 int gsp_aa_node_weights(const gsp_graph* g, double* d_node_w, void* stream);
+/* d_node_w[u] = d_table[deg(u)]: node weights from a caller-supplied per-degree table of max_degree + 1 entries (the host
+ * evaluates the reference's NumPy expression once per distinct degree; keeps the libm-defined last bit). */
+int gsp_aa_node_weights_from_table(const gsp_graph* g, const double* d_table, int64_t table_len, double* d_node_w,
+                                   void* stream);
 
 /* Owner-sharded variants for multi-GPU scoring of a SYMMETRIC graph: every undirected pair {u,v} is evaluated on
  * exactly one rank — the one whose node range [node_begin, node_end) holds the pair's owner (the endpoint with the
