@@ -34,60 +34,89 @@ struct CgColumns {        // per-column solver state, arrays of length k
     int32_t* iters;
 };
 
+// Lane -> (row slot, column). With k >= 32 a warp works on one row and a strip of 32 columns (blockIdx.y picks the
+// strip). With k < 32 (projection columns sharded over several GPUs leave 8 or 16 per rank) the columns are padded to
+// kc = 2^ceil(log2 k) and a warp works on 32/kc rows at once, so no lane idles and a row's kc values are one
+// contiguous request.
+struct LaneMap {
+    int c;        // column of this lane
+    int sub;      // row slot inside the warp
+    int rows;     // rows per warp pass
+    int kc;       // padded columns per row slot (32 in strip mode)
+    bool col_ok;
+};
+
+__device__ __forceinline__ LaneMap lane_map(int k) {
+    LaneMap m;
+    const int lane = lane_id();
+    if (k >= kWarp) {
+        m.c = blockIdx.y * kWarp + lane; m.sub = 0; m.rows = 1; m.kc = kWarp;
+    } else {
+        int kc = 1;
+        while (kc < k) kc <<= 1;
+        m.c = lane & (kc - 1); m.sub = lane / kc; m.rows = kWarp / kc; m.kc = kc;
+    }
+    m.col_ok = m.c < k;
+    return m;
+}
+
 // Y[u, c] = sum over incident undirected edges e (ascending e) of +-R[e, c]   (metrics.py:260-275).
 __global__ void __launch_bounds__(kThreads)
 project_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                const int32_t* __restrict__ und_id, const double* __restrict__ R, int64_t ldr, int k,
                double* __restrict__ Y) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    const bool col_ok = c < k;
+    const LaneMap m = lane_map(k);
     const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-    for (int64_t u = warp; u < n; u += nwarps) {
+    for (int64_t base = warp * m.rows; base < n; base += nwarps * m.rows) {
+        const int64_t u = base + m.sub;
+        if (u >= n) continue;
         double acc = 0.0;
         const int64_t p0 = indptr[u], p1 = indptr[u + 1];
         for (int64_t p = p0; p < p1; ++p) {
             const int32_t e = __ldg(und_id + p);
             if (e < 0) continue;                                    // self loop / unmatched direction
             const int32_t v = __ldg(indices + p);
-            if (col_ok) {
-                const double r = __ldg(R + (int64_t)e * ldr + c);
+            if (m.col_ok) {
+                const double r = __ldg(R + (int64_t)e * ldr + m.c);
                 acc = (u < v) ? __dadd_rn(acc, r) : __dsub_rn(acc, r);   // +1 * r / -1 * r are exact
             }
         }
-        if (col_ok) Y[u * (int64_t)k + c] = acc;
+        if (m.col_ok) Y[u * (int64_t)k + m.c] = acc;
     }
 }
 
-// Deterministic column reduction helper: every block writes partial[blockIdx.x][c]; warps of a block are
-// combined in fixed order through shared memory.
-__device__ __forceinline__ void block_column_partial(double lane_sum, bool col_ok, int c, int k, double* partial) {
+// Deterministic column reduction: row slots of a warp are combined with a fixed xor tree, warps of a block in fixed
+// order through shared memory, and every block writes partial[blockIdx.x][c].
+__device__ __forceinline__ void block_column_partial(double lane_sum, const LaneMap& m, int k, double* partial) {
     __shared__ double sh[kWarps][kWarp];
+    for (int off = kWarp / 2; off >= m.kc; off >>= 1) lane_sum = __dadd_rn(lane_sum, __shfl_xor_sync(0xffffffffu, lane_sum, off));
     const int w = threadIdx.x >> 5, l = lane_id();
     sh[w][l] = lane_sum;
     __syncthreads();
-    if (w == 0 && col_ok) {
+    if (w == 0 && m.sub == 0 && m.col_ok) {
         double s = sh[0][l];
 #pragma unroll
         for (int i = 1; i < kWarps; ++i) s = __dadd_rn(s, sh[i][l]);
-        partial[(int64_t)blockIdx.x * k + c] = s;
+        partial[(int64_t)blockIdx.x * k + m.c] = s;
     }
 }
 
 // r = Y (aliased), x = 0, partial column sums of b^2.
 __global__ void __launch_bounds__(kThreads)
 init_kernel(int64_t n, int k, const double* __restrict__ r, double* __restrict__ x, double* __restrict__ partial) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    const bool col_ok = c < k;
+    const LaneMap m = lane_map(k);
     double s = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
-        if (col_ok) {
-            const double b = r[i * (int64_t)k + c];
-            x[i * (int64_t)k + c] = 0.0;
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    for (int64_t base = warp * m.rows; base < n; base += (int64_t)gridDim.x * kWarps * m.rows) {
+        const int64_t i = base + m.sub;
+        if (i < n && m.col_ok) {
+            const double b = r[i * (int64_t)k + m.c];
+            x[i * (int64_t)k + m.c] = 0.0;
             s = __dadd_rn(s, __dmul_rn(b, b));
         }
     }
-    block_column_partial(s, col_ok, c, k, partial);
+    block_column_partial(s, m, k, partial);
 }
 
 // Column finalisation at the TOP of iteration `it`: rr = sum of partials; convergence test; beta.
@@ -123,22 +152,25 @@ __global__ void top_kernel(int k, int nblocks, const double* __restrict__ partia
 // p = r + beta * p   (first iteration: p = r)
 __global__ void __launch_bounds__(kThreads)
 direction_kernel(int64_t n, int k, const double* __restrict__ r, double* __restrict__ p, CgColumns cg, int it) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    if (c >= k || !cg.active[c]) return;
-    const double beta = cg.beta[c];
-    for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
-        const int64_t o = i * (int64_t)k + c;
+    const LaneMap m = lane_map(k);
+    if (!m.col_ok || !cg.active[m.c]) return;
+    const double beta = cg.beta[m.c];
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    for (int64_t base = warp * m.rows; base < n; base += (int64_t)gridDim.x * kWarps * m.rows) {
+        const int64_t i = base + m.sub;
+        if (i >= n) continue;
+        const int64_t o = i * (int64_t)k + m.c;
         p[o] = it > 0 ? __dadd_rn(__dmul_rn(p[o], beta), r[o]) : r[o];
     }
 }
 
-// q = (D - A + reg I) p for a 32-column strip, fused with the p.q column partials.
+// q = (D - A + reg I) p, fused with the p.q column partials.
 //
 // Work items are row SEGMENTS of at most kSeg neighbours (a row of degree d has max(1, ceil(d/kSeg)) of them), one
-// warp per item, so a hub row with 10^5 neighbours is spread over hundreds of warps instead of serialising one.
-// Rows with a single segment (almost all) are finished here in csr_matvec's exact order (neighbours ascending, the
-// diagonal at its sorted position). For longer rows segment 0 parks its partial sum in q[i] and the others in
-// `segpart`; spmm_combine_kernel adds them in segment order. Indices and p values are fetched four deep.
+// row slot of a warp per item, so a hub row with 10^5 neighbours is spread over hundreds of warps instead of
+// serialising one. Rows with a single segment (almost all) are finished here in csr_matvec's exact order (neighbours
+// ascending, the diagonal at its sorted position). For longer rows segment 0 parks its partial sum in q[i] and the
+// others in `segpart`; spmm_combine_kernel adds them in segment order. Indices and p values are fetched four deep.
 constexpr int kSeg = 512;
 
 struct SegItem {
@@ -151,29 +183,33 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
                 const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
                 double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    const bool col_ok = c < k && active[c];
+    const LaneMap m = lane_map(k);
+    const bool col_ok = m.col_ok && active[m.c];
     double dot = 0.0;
-    if (__any_sync(0xffffffffu, col_ok)) {  // a strip whose 32 columns have all stopped does no work
-        for (int64_t it = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); it < num_items; it += (int64_t)gridDim.x * kWarps) {
-            const int32_t i = items[it].row;
-            const int seg = items[it].seg;
+    if (__any_sync(0xffffffffu, col_ok)) {  // a warp whose columns have all stopped does no work
+        const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+        for (int64_t base = warp * m.rows; base < num_items; base += (int64_t)gridDim.x * kWarps * m.rows) {
+            const int64_t it = base + m.sub;
+            const bool item_ok = it < num_items;
+            const int32_t i = item_ok ? items[it].row : 0;
+            const int seg = item_ok ? items[it].seg : 0;
             const int64_t row0 = indptr[i], row1 = indptr[i + 1];
-            const int64_t p0 = row0 + (int64_t)seg * kSeg;
-            const int64_t p1 = min(p0 + kSeg, row1);
+            const int64_t p0 = item_ok ? row0 + (int64_t)seg * kSeg : 0;
+            const int64_t p1 = item_ok ? min(p0 + kSeg, row1) : 0;
             const bool single = row1 - row0 <= kSeg;
-            const double pi = (col_ok && single) ? p[i * (int64_t)k + c] : 0.0;
+            const bool lane_ok = col_ok && item_ok;
+            const double pi = (lane_ok && single) ? p[i * (int64_t)k + m.c] : 0.0;
             const double dterm = __dmul_rn(diag[i], pi);
             double s = 0.0;
             bool placed = !single;                  // multi-segment rows: the diagonal is added by the combine kernel
-            for (int64_t t0 = p0; t0 < p1; t0 += 4) {
+            for (int64_t t0 = p0; __any_sync(0xffffffffu, t0 < p1); t0 += 4) {   // row slots may differ in length
                 int32_t j[4];
                 double pj[4], a[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) j[u] = t0 + u < p1 ? __ldg(indices + t0 + u) : -1;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    pj[u] = (col_ok && j[u] >= 0) ? __ldg(p + (int64_t)j[u] * k + c) : 0.0;
+                    pj[u] = (lane_ok && j[u] >= 0) ? __ldg(p + (int64_t)j[u] * k + m.c) : 0.0;
                     a[u] = (data && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
                 }
 #pragma unroll
@@ -188,20 +224,20 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
                 }
             }
             if (!placed) s = __dadd_rn(s, dterm);
-            if (col_ok) {
+            if (lane_ok) {
                 if (single) {
-                    q[i * (int64_t)k + c] = s;
+                    q[i * (int64_t)k + m.c] = s;
                     dot = __dadd_rn(dot, __dmul_rn(pi, s));
                 } else if (seg == 0) {
-                    q[i * (int64_t)k + c] = s;
+                    q[i * (int64_t)k + m.c] = s;
                 } else {   // extra segments of all rows are numbered consecutively: (items before row i) - i + seg - 1
                     const int64_t slot = (i ? seg_incl[i - 1] : 0) - i + seg - 1;
-                    segpart[slot * k + c] = s;
+                    segpart[slot * k + m.c] = s;
                 }
             }
         }
     }
-    block_column_partial(dot, c < k, c, k, partial);
+    block_column_partial(dot, m, k, partial);
 }
 
 // Rows longer than kSeg: q[i] = seg0 + diag*p_i + seg1 + seg2 + ...   and their share of p.q
@@ -209,25 +245,23 @@ __global__ void __launch_bounds__(kThreads)
 spmm_combine_kernel(int64_t n, const int64_t* __restrict__ seg_incl, const int64_t* __restrict__ indptr,
                     const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
                     const double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    const bool col_ok = c < k && active[c];
+    const LaneMap m = lane_map(k);
+    const bool col_ok = m.col_ok && active[m.c];
     double dot = 0.0;
-    if (__any_sync(0xffffffffu, col_ok)) {
-        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
-            if (indptr[i + 1] - indptr[i] <= kSeg) continue;
-            const int64_t before = i ? seg_incl[i - 1] : 0;
-            const int64_t nseg = seg_incl[i] - before;
-            if (col_ok) {
-                const double pi = p[i * (int64_t)k + c];
-                double s = __dadd_rn(q[i * (int64_t)k + c], __dmul_rn(diag[i], pi));
-                const int64_t slot0 = before - i;
-                for (int64_t sg = 1; sg < nseg; ++sg) s = __dadd_rn(s, segpart[(slot0 + sg - 1) * k + c]);
-                q[i * (int64_t)k + c] = s;
-                dot = __dadd_rn(dot, __dmul_rn(pi, s));
-            }
-        }
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    for (int64_t base = warp * m.rows; base < n; base += (int64_t)gridDim.x * kWarps * m.rows) {
+        const int64_t i = base + m.sub;
+        if (i >= n || !col_ok || indptr[i + 1] - indptr[i] <= kSeg) continue;
+        const int64_t before = i ? seg_incl[i - 1] : 0;
+        const int64_t nseg = seg_incl[i] - before;
+        const double pi = p[i * (int64_t)k + m.c];
+        double s = __dadd_rn(q[i * (int64_t)k + m.c], __dmul_rn(diag[i], pi));
+        const int64_t slot0 = before - i;
+        for (int64_t sg = 1; sg < nseg; ++sg) s = __dadd_rn(s, segpart[(slot0 + sg - 1) * k + m.c]);
+        q[i * (int64_t)k + m.c] = s;
+        dot = __dadd_rn(dot, __dmul_rn(pi, s));
     }
-    block_column_partial(dot, c < k, c, k, partial);
+    block_column_partial(dot, m, k, partial);
 }
 
 __global__ void seg_count_kernel(int64_t n, const int64_t* __restrict__ indptr, int64_t* __restrict__ counts) {
@@ -258,20 +292,23 @@ __global__ void alpha_kernel(int k, int nblocks, const double* __restrict__ part
 __global__ void __launch_bounds__(kThreads)
 update_kernel(int64_t n, int k, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
               double* __restrict__ r, CgColumns cg, double* __restrict__ partial) {
-    const int c = blockIdx.y * kWarp + lane_id();
-    const bool col_ok = c < k && cg.active[c];
+    const LaneMap m = lane_map(k);
+    const bool col_ok = m.col_ok && cg.active[m.c];
     double s = 0.0;
     if (col_ok) {
-        const double alpha = cg.alpha[c];
-        for (int64_t i = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5); i < n; i += (int64_t)gridDim.x * kWarps) {
-            const int64_t o = i * (int64_t)k + c;
+        const double alpha = cg.alpha[m.c];
+        const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+        for (int64_t base = warp * m.rows; base < n; base += (int64_t)gridDim.x * kWarps * m.rows) {
+            const int64_t i = base + m.sub;
+            if (i >= n) continue;
+            const int64_t o = i * (int64_t)k + m.c;
             x[o] = __dadd_rn(x[o], __dmul_rn(alpha, p[o]));
             const double rn = __dsub_rn(r[o], __dmul_rn(alpha, q[o]));
             r[o] = rn;
             s = __dadd_rn(s, __dmul_rn(rn, rn));
         }
     }
-    block_column_partial(s, c < k, c, k, partial);
+    block_column_partial(s, m, k, partial);
 }
 
 __global__ void diag_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -291,22 +328,28 @@ __global__ void diag_kernel(int64_t n, const int64_t* __restrict__ indptr, const
 __global__ void __launch_bounds__(kThreads)
 resistance_kernel(int64_t e_begin, int64_t e_end, const int32_t* __restrict__ rows, const int32_t* __restrict__ indices,
                   const double* __restrict__ z, int k, double* __restrict__ out) {
-    const int lane = lane_id();
+    // lanes of a slot cover the columns (stride kc); small k packs 32/kc edges into one warp
+    int kc = kWarp;
+    if (k < kWarp) { kc = 1; while (kc < k) kc <<= 1; }
+    const int lane = lane_id(), c0 = lane & (kc - 1), sub = lane / kc, per = kWarp / kc;
     const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-    for (int64_t e = e_begin + warp; e < e_end; e += nwarps) {
-        const double* zu = z + (int64_t)__ldg(rows + e) * k;
-        const double* zv = z + (int64_t)__ldg(indices + e) * k;
+    for (int64_t base = e_begin + warp * per; base < e_end; base += nwarps * per) {
+        const int64_t e = base + sub;
         double s = 0.0;
-        for (int c = lane; c < k; c += kWarp) {
-            double a = __ldg(zu + c), b = __ldg(zv + c);
-            if (!isfinite(a)) a = 0.0;
-            if (!isfinite(b)) b = 0.0;
-            const double d = __dsub_rn(a, b);
-            s = __dadd_rn(s, __dmul_rn(d, d));
+        if (e < e_end) {
+            const double* zu = z + (int64_t)__ldg(rows + e) * k;
+            const double* zv = z + (int64_t)__ldg(indices + e) * k;
+            for (int c = c0; c < k; c += kc) {
+                double a = __ldg(zu + c), b = __ldg(zv + c);
+                if (!isfinite(a)) a = 0.0;
+                if (!isfinite(b)) b = 0.0;
+                const double d = __dsub_rn(a, b);
+                s = __dadd_rn(s, __dmul_rn(d, d));
+            }
         }
-        for (int o = 16; o; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-        if (lane == 0) out[e - e_begin] = s;
+        for (int o = kc / 2; o; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (e < e_end && c0 == 0) out[e - e_begin] = s;
     }
 }
 
@@ -381,7 +424,7 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     if (int rc = ensure_segments(g, s)) return rc;
     const int64_t extra_segments = g->num_seg_items - n;   // > 0 when some row is longer than kSeg
 
-    const int strips = (k + kWarp - 1) / kWarp;
+    const int strips = k >= kWarp ? (k + kWarp - 1) / kWarp : 1;   // k < 32: several rows per warp instead of strips
     // row blocks: enough CTAs for >= 8 per SM over all strips, at most one warp-row each
     int64_t row_blocks = (static_cast<int64_t>(kNumSMs) * 8 + strips - 1) / strips;
     const int64_t max_rb = (n + kWarps - 1) / kWarps;
@@ -447,7 +490,7 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     }
     if (e_end > e_begin) {
         const int64_t edges = e_end - e_begin;
-        resistance_kernel<<<grid_for(edges, kWarps, 8), kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, x.ptr, k,
+        resistance_kernel<<<grid_for(edges, kWarps, 16), kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, x.ptr, k,
                                                                          d_partial);
         GSP_CHECK_LAUNCH();
     }
