@@ -61,18 +61,30 @@ __device__ __forceinline__ LaneMap lane_map(int k) {
 }
 
 // Y[u, c] = sum over incident undirected edges e (ascending e) of +-R[e, c]   (metrics.py:260-275).
+// Same row-segment work items as the SpMM (a hub row's 10^5 incident edges are spread over many warps); rows longer
+// than one segment are finished by project_combine_kernel in segment order.
+struct SegItem {
+    int32_t row;
+    int32_t seg;   // segment index inside the row
+};
+constexpr int kSeg = 512;
+
 __global__ void __launch_bounds__(kThreads)
-project_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+project_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
+               const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                const int32_t* __restrict__ und_id, const double* __restrict__ R, int64_t ldr, int k,
-               double* __restrict__ Y) {
+               double* __restrict__ Y, double* __restrict__ segpart) {
     const LaneMap m = lane_map(k);
     const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-    for (int64_t base = warp * m.rows; base < n; base += nwarps * m.rows) {
-        const int64_t u = base + m.sub;
-        if (u >= n) continue;
+    for (int64_t base = warp * m.rows; base < num_items; base += nwarps * m.rows) {
+        const int64_t it = base + m.sub;
+        if (it >= num_items) continue;
+        const int64_t u = items[it].row;
+        const int seg = items[it].seg;
+        const int64_t p0 = indptr[u] + (int64_t)seg * kSeg;
+        const int64_t p1 = min(p0 + kSeg, indptr[u + 1]);
         double acc = 0.0;
-        const int64_t p0 = indptr[u], p1 = indptr[u + 1];
         for (int64_t p = p0; p < p1; ++p) {
             const int32_t e = __ldg(und_id + p);
             if (e < 0) continue;                                    // self loop / unmatched direction
@@ -82,7 +94,26 @@ project_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __r
                 acc = (u < v) ? __dadd_rn(acc, r) : __dsub_rn(acc, r);   // +1 * r / -1 * r are exact
             }
         }
-        if (m.col_ok) Y[u * (int64_t)k + m.c] = acc;
+        if (m.col_ok) {
+            if (seg == 0) Y[u * (int64_t)k + m.c] = acc;
+            else segpart[((u ? seg_incl[u - 1] : 0) - u + seg - 1) * k + m.c] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+project_combine_kernel(int64_t n, const int64_t* __restrict__ seg_incl, const int64_t* __restrict__ indptr, int k,
+                       double* __restrict__ Y, const double* __restrict__ segpart) {
+    const LaneMap m = lane_map(k);
+    const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+    for (int64_t base = warp * m.rows; base < n; base += (int64_t)gridDim.x * kWarps * m.rows) {
+        const int64_t i = base + m.sub;
+        if (i >= n || !m.col_ok || indptr[i + 1] - indptr[i] <= kSeg) continue;
+        const int64_t before = i ? seg_incl[i - 1] : 0;
+        const int64_t nseg = seg_incl[i] - before;
+        double s = Y[i * (int64_t)k + m.c];
+        for (int64_t sg = 1; sg < nseg; ++sg) s = __dadd_rn(s, segpart[(before - i + sg - 1) * k + m.c]);
+        Y[i * (int64_t)k + m.c] = s;
     }
 }
 
@@ -100,6 +131,7 @@ __device__ __forceinline__ void block_column_partial(double lane_sum, const Lane
         for (int i = 1; i < kWarps; ++i) s = __dadd_rn(s, sh[i][l]);
         partial[(int64_t)blockIdx.x * k + m.c] = s;
     }
+    __syncthreads();   // the staging array may be reused right away
 }
 
 // r = Y (aliased), x = 0, partial column sums of b^2.
@@ -171,13 +203,6 @@ direction_kernel(int64_t n, int k, const double* __restrict__ r, double* __restr
 // serialising one. Rows with a single segment (almost all) are finished here in csr_matvec's exact order (neighbours
 // ascending, the diagonal at its sorted position). For longer rows segment 0 parks its partial sum in q[i] and the
 // others in `segpart`; spmm_combine_kernel adds them in segment order. Indices and p values are fetched four deep.
-constexpr int kSeg = 512;
-
-struct SegItem {
-    int32_t row;
-    int32_t seg;   // segment index inside the row
-};
-
 __global__ void __launch_bounds__(kThreads)
 spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
@@ -238,6 +263,78 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
         }
     }
     block_column_partial(dot, m, k, partial);
+}
+
+// Two adjacent columns per lane (k % 64 == 0): one warp covers a 64-column strip with 16-byte gathers, so the index
+// list of a row is read once per 64 columns instead of once per 32 and half as many load instructions are issued.
+__global__ void __launch_bounds__(kThreads)
+spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
+                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
+                 const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
+                 double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
+    const int c = blockIdx.y * 64 + 2 * lane_id();
+    const bool any_active = active[c] | active[c + 1];
+    double dot0 = 0.0, dot1 = 0.0;
+    if (__any_sync(0xffffffffu, any_active)) {
+        const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+        for (int64_t it = warp; it < num_items; it += (int64_t)gridDim.x * kWarps) {
+            const int32_t i = items[it].row;
+            const int seg = items[it].seg;
+            const int64_t row0 = indptr[i], row1 = indptr[i + 1];
+            const int64_t p0 = row0 + (int64_t)seg * kSeg;
+            const int64_t p1 = min(p0 + kSeg, row1);
+            const bool single = row1 - row0 <= kSeg;
+            double2 pi = make_double2(0.0, 0.0);
+            if (single) pi = *reinterpret_cast<const double2*>(p + i * (int64_t)k + c);
+            const double di = diag[i];
+            const double d0 = __dmul_rn(di, pi.x), d1 = __dmul_rn(di, pi.y);
+            double s0 = 0.0, s1 = 0.0;
+            bool placed = !single;
+            for (int64_t t0 = p0; t0 < p1; t0 += 4) {
+                int32_t j[4];
+                double2 pj[4];
+                double a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) j[u] = t0 + u < p1 ? __ldg(indices + t0 + u) : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pj[u] = j[u] >= 0 ? __ldg(reinterpret_cast<const double2*>(p + (int64_t)j[u] * k + c)) : make_double2(0.0, 0.0);
+                    a[u] = (data && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (j[u] < 0) break;
+                    if (j[u] == i) {
+                        if (!placed) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); placed = true; }
+                        continue;
+                    }
+                    if (!placed && j[u] > i) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); placed = true; }
+                    if (data) {
+                        s0 = __dadd_rn(s0, __dmul_rn(-a[u], pj[u].x));
+                        s1 = __dadd_rn(s1, __dmul_rn(-a[u], pj[u].y));
+                    } else {
+                        s0 = __dsub_rn(s0, pj[u].x);
+                        s1 = __dsub_rn(s1, pj[u].y);
+                    }
+                }
+            }
+            if (!placed) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); }
+            if (single || seg == 0) {
+                *reinterpret_cast<double2*>(q + i * (int64_t)k + c) = make_double2(s0, s1);
+                if (single) {
+                    dot0 = __dadd_rn(dot0, __dmul_rn(pi.x, s0));
+                    dot1 = __dadd_rn(dot1, __dmul_rn(pi.y, s1));
+                }
+            } else {
+                const int64_t slot = (i ? seg_incl[i - 1] : 0) - i + seg - 1;
+                *reinterpret_cast<double2*>(segpart + slot * k + c) = make_double2(s0, s1);
+            }
+        }
+    }
+    LaneMap m{c, 0, 1, kWarp, true};
+    block_column_partial(dot0, m, k, partial);
+    m.c = c + 1;
+    block_column_partial(dot1, m, k, partial);
 }
 
 // Rows longer than kSeg: q[i] = seg0 + diag*p_i + seg1 + seg2 + ...   and their share of p.q
@@ -455,8 +552,14 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
 
     diag_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, g->indptr, g->indices, g->data, reg, diag.ptr);
     GSP_CHECK_LAUNCH();
-    project_kernel<<<grid2d, kThreads, 0, s>>>(n, g->indptr, g->indices, g->und_id, d_R, ldr, k, r.ptr);
+    const SegItem* seg_items = reinterpret_cast<const SegItem*>(g->seg_items);
+    project_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->und_id, d_R,
+                                               ldr, k, r.ptr, segpart.ptr);
     GSP_CHECK_LAUNCH();
+    if (extra_segments > 0) {
+        project_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, k, r.ptr, segpart.ptr);
+        GSP_CHECK_LAUNCH();
+    }
     init_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, x.ptr, partial.ptr);
     GSP_CHECK_LAUNCH();
     const int col_blocks = (k + 127) / 128;
@@ -474,9 +577,14 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
         GSP_CHECK_LAUNCH();
         direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
         GSP_CHECK_LAUNCH();
-        spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(reinterpret_cast<const SegItem*>(g->seg_items), g->num_seg_items, g->seg_incl,
-                                                   g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,
-                                                   cg.active, partial.ptr);
+        if (k % 64 == 0) {   // 64-column strips, two columns per lane
+            spmm_dot2_kernel<<<dim3((unsigned)row_blocks, (unsigned)(k / 64)), kThreads, 0, s>>>(
+                seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,
+                cg.active, partial.ptr);
+        } else {
+            spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->data,
+                                                       diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active, partial.ptr);
+        }
         GSP_CHECK_LAUNCH();
         if (extra_segments > 0) {
             spmm_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,

@@ -483,7 +483,7 @@ def test_owner_sharded_scoring_sums_to_the_full_result():
     assert slices[0][0] == 0 and slices[-1][1] == g.nnz and length * 3 >= g.nnz
 
 
-@pytest.mark.parametrize("k", [1, 3, 8, 12, 16, 31, 32, 33, 70])
+@pytest.mark.parametrize("k", [1, 3, 8, 12, 16, 31, 32, 33, 64, 70, 128])
 def test_approx_er_any_column_count(k):
     """k < 32 packs several rows per warp, k >= 32 uses 32-column strips: both against the oracle (hub rows > 512 too)."""
     from gsr_b200.metrics import _approx_er_on_graph
