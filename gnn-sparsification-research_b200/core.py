@@ -261,11 +261,34 @@ class GraphSparsifier:
             "edge-scoring hot path this engine accelerates (SURVEY §8f-3); `_scores_to_cost` is provided."
         )
 
-    def sparsify_sampled(self, metric: str, retention_ratio: float, seed: int = 42, return_mask: bool = False):
-        """Sample edges without replacement with probability proportional to score (reference core.py:281-357)."""
+    def sparsify_sampled(self, metric: str, retention_ratio: float, seed: int = 42, return_mask: bool = False,
+                         method: str = "numpy"):
+        """Sample edges without replacement with probability proportional to score (reference core.py:281-357).
+
+        `method="numpy"` (default) reproduces the reference's draw bit for bit: NumPy's PCG64 `Generator.choice`
+        with its sequential fp64 cumsum runs on the host (an RNG stream is observable behaviour). `method="device"`
+        is an opt-in extension that never leaves the GPU: Efraimidis-Spirakis keys u^(1/p) (u ~ torch Philox) and the
+        radix select — the same sampling distribution (successive weighted draws without replacement), a different
+        random stream, so not mask-identical to the reference."""
         self._check_ratio(retention_ratio)
         if retention_ratio == 1.0:
             return self._full(return_mask)
+        if method == "device":
+            scores = self._device_scores(metric)
+            if scores.numel() != self.num_edges:
+                raise ValueError("'a' and 'p' must have same size")
+            floor = 1e-8
+            p = torch.nan_to_num(scores, nan=floor, posinf=floor, neginf=floor).clamp_min(floor)
+            gen = torch.Generator(device=p.device)
+            gen.manual_seed(int(seed))
+            u = torch.rand(p.shape, dtype=torch.float64, device=p.device, generator=gen).clamp_min(1e-300)
+            keys = torch.log(u) / p                                   # log of u^(1/p): larger = drawn earlier
+            num_keep = int(self.num_edges * retention_ratio)
+            mask_dev, kept = self._threshold_mask(keys, num_keep, keep_lowest=False) if num_keep > 0 else (
+                torch.zeros(self.num_edges, dtype=torch.uint8, device=p.device), 0)
+            return self._finish(mask_dev, kept, return_mask)
+        if method != "numpy":
+            raise ValueError("method must be 'numpy' or 'device'")
         rng = np.random.default_rng(seed)
         scores = self.compute_scores(metric)
         floor = 1e-8

@@ -72,3 +72,21 @@ def sparsify_by_composite(sparsifier, metric: str, retention_ratio: float):
     if strategy == "metric_backbone":
         return sparsifier.sparsify_metric_backbone(base)[0]
     raise ValueError(f"Unknown strategy: {strategy}")
+
+
+def compute_edge_weights(data, metric: str = "jaccard", device: str = "cuda"):
+    """Second "-W" convention of the reference (`src/experiments/ablation.py:119-145`): re-score the (already
+    sparsified) graph `data`, min-max normalise over ALL its edges, clip to [0.1, 1], float32 on `device`.
+    Scores come from the GPU engine; the normalisation runs on the device in fp64 like the NumPy original."""
+    from .core import GraphSparsifier
+
+    sp = GraphSparsifier(data, device)
+    scores = sp._device_scores(metric)
+    if scores.numel() == 0:
+        return torch.empty(0, dtype=torch.float32, device=device)
+    lo, hi = scores.min(), scores.max()
+    if bool(hi > lo):
+        normalized = (scores - lo) / (hi - lo)
+    else:
+        normalized = torch.ones_like(scores)
+    return normalized.clamp(0.1, 1.0).to(torch.float32).to(device)

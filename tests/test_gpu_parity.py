@@ -497,3 +497,25 @@ def test_approx_er_any_column_count(k):
     # absolute error (1e-6 of the largest value); everything else meets the 1e-4 relative bar
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-6 * want.max())
     assert np.abs(iters.cpu().numpy() - want_iters).max() <= max(3, 0.05 * want_iters.max())
+
+
+def test_device_sampling_and_second_weight_convention():
+    ei, x, n = named_graph("cora")
+    e = ei.shape[1]
+    sp = make_sparsifier(ei, n, x, device=DEV)
+    jac = sp.compute_scores("jaccard")
+    out, mask = sp.sparsify_sampled("jaccard", 0.3, seed=7, return_mask=True, method="device")
+    out2, mask2 = sp.sparsify_sampled("jaccard", 0.3, seed=7, return_mask=True, method="device")
+    m = mask.numpy()
+    assert m.sum() == int(e * 0.3) == out.edge_index.size(1) and torch.equal(mask, mask2)
+    assert not torch.equal(mask, sp.sparsify_sampled("jaccard", 0.3, seed=8, return_mask=True, method="device")[1])
+    assert jac[m].mean() > 1.5 * jac[~m].mean()            # sampling proportional to score favours high scores
+    with pytest.raises(ValueError):
+        sp.sparsify_sampled("jaccard", 0.3, method="bogus")
+    # ablation.py:119-145 — re-score the sparse graph, min-max over all its edges, clip to [0.1, 1]
+    sparse = sp.sparsify("jaccard", 0.6)
+    w = labels.compute_edge_weights(sparse, "jaccard", DEV)
+    sub = sparse.edge_index.cpu().numpy()
+    s = co.calculate_jaccard_scores(co.csr_from_edge_index(sub, n))
+    want = np.clip((s - s.min()) / (s.max() - s.min()), 0.1, 1.0).astype(np.float32)
+    assert bits_equal(w.cpu().numpy(), want)
