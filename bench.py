@@ -422,6 +422,18 @@ def main() -> None:
                 "note": "algorithmic bytes of the owner-hashed schedule (DESIGN.md); SURVEY 8d formula in per_method[*].survey_formula_frac; "
                         "duration = CUDA events on the launching stream around the scoring call"}
 
+    # DRAM traffic of the dominant kernel from the committed ncu capture (only valid for the workload it was taken on)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        w = traffic["workload"]
+        if (w["scale"], w["edge_factor"], w["dim"], w["n_gpus"]) == (args.scale, args.edge_factor, args.dim, world) and dominant in traffic:
+            roofline["traffic"] = traffic[dominant]["dram_bytes_per_launch"] / 1e9
+            roofline["traffic_unit"] = "GB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roofline["traffic_kernel"] = traffic[dominant]["kernel"]
+            roofline["algorithmic_gb"] = per_kernel[dominant]["alg_gb"]
+    except Exception:
+        pass
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         adj, xs, es = cpu_sample_inputs()
