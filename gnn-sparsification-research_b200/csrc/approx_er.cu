@@ -267,7 +267,10 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
 
 // Two adjacent columns per lane (k % 64 == 0): one warp covers a 64-column strip with 16-byte gathers, so the index
 // list of a row is read once per 64 columns instead of once per 32 and half as many load instructions are issued.
-__global__ void __launch_bounds__(kThreads)
+// The neighbour ids of the next four-deep step are fetched while the current step's gathers are in flight (the first
+// version serialised "load ids -> gather p -> consume" and ran at 30 % occupancy / 12 % of the L2->SM path, ncu).
+template <bool kHasData>
+__global__ void __launch_bounds__(kThreads, 4)
 spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
                  const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
@@ -284,6 +287,9 @@ spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int
             const int64_t p0 = row0 + (int64_t)seg * kSeg;
             const int64_t p1 = min(p0 + kSeg, row1);
             const bool single = row1 - row0 <= kSeg;
+            int32_t jn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jn[u] = p0 + u < p1 ? __ldg(indices + p0 + u) : -1;
             double2 pi = make_double2(0.0, 0.0);
             if (single) pi = *reinterpret_cast<const double2*>(p + i * (int64_t)k + c);
             const double di = diag[i];
@@ -295,12 +301,13 @@ spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int
                 double2 pj[4];
                 double a[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) j[u] = t0 + u < p1 ? __ldg(indices + t0 + u) : -1;
-#pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    j[u] = jn[u];
                     pj[u] = j[u] >= 0 ? __ldg(reinterpret_cast<const double2*>(p + (int64_t)j[u] * k + c)) : make_double2(0.0, 0.0);
-                    a[u] = (data && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
+                    a[u] = (kHasData && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) jn[u] = t0 + 4 + u < p1 ? __ldg(indices + t0 + 4 + u) : -1;   // next step's ids
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (j[u] < 0) break;
@@ -309,7 +316,7 @@ spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int
                         continue;
                     }
                     if (!placed && j[u] > i) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); placed = true; }
-                    if (data) {
+                    if (kHasData) {
                         s0 = __dadd_rn(s0, __dmul_rn(-a[u], pj[u].x));
                         s1 = __dadd_rn(s1, __dmul_rn(-a[u], pj[u].y));
                     } else {
@@ -578,9 +585,16 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
         direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
         GSP_CHECK_LAUNCH();
         if (k % 64 == 0) {   // 64-column strips, two columns per lane
-            spmm_dot2_kernel<<<dim3((unsigned)row_blocks, (unsigned)(k / 64)), kThreads, 0, s>>>(
-                seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr,
-                cg.active, partial.ptr);
+            const dim3 grid64((unsigned)row_blocks, (unsigned)(k / 64));
+            if (g->data) {
+                spmm_dot2_kernel<true><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices,
+                                                                  g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,
+                                                                  partial.ptr);
+            } else {
+                spmm_dot2_kernel<false><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices,
+                                                                   nullptr, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,
+                                                                   partial.ptr);
+            }
         } else {
             spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->data,
                                                        diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active, partial.ptr);

@@ -61,6 +61,7 @@ __device__ __forceinline__ bool hash_contains(const int32_t* slots, uint32_t mas
 // linear-probing version showed ~50 % of all issued instructions in its probe loop at 3-8 active lanes.
 // Keys that cannot be placed after kCuckooMaxKicks evictions go to a small stash that lookups scan only when it
 // is non-empty; if even the stash overflows the tile is rebuilt with the next pair of multipliers.
+constexpr int kJaccardDepth = 8;   // Jaccard streams long rows eight groups deep (counts need no ordering)
 constexpr int kCuckooMaxKicks = 64;
 constexpr int kStashMax = 32;
 
@@ -297,13 +298,14 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
     const int lane = lane_id();
     int c = 0;
     if (!kBounded) {
-        for (int top = cursor - 1 - lane; top + lane >= 0; top -= 4 * kWarp) {
-            int32_t x[4];
+        constexpr int D = kMode == 0 ? kJaccardDepth : 4;   // 32-id groups fetched per round
+        for (int top = cursor - 1 - lane; top + lane >= 0; top -= D * kWarp) {
+            int32_t x[D];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
+            for (int k = 0; k < D; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
             if (kMode == 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < D; ++k) {
                     if (k > 0 && top + lane - k * kWarp < 0) break;   // whole group below the row start (warp-uniform)
                     c += cuckoo_contains(table, x[k]);
                     if (x[k] == o) rev = top - k * kWarp;
@@ -311,17 +313,17 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
             } else {
                 // probe all four groups, then issue all weight gathers, then accumulate in order: the gather latency
                 // of a round is paid once instead of once per group
-                bool hit[4];
-                double w[4];
+                bool hit[D];
+                double w[D];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < D; ++k) {
                     hit[k] = cuckoo_contains(table, x[k]);
                     if (x[k] == o) rev = top - k * kWarp;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
+                for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) accumulate_hits<kMode>(hit[k], w[k], queue, acc);
+                for (int k = 0; k < D; ++k) accumulate_hits<kMode>(hit[k], w[k], queue, acc);
             }
         }
         cursor = 0;

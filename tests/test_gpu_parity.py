@@ -519,3 +519,36 @@ def test_device_sampling_and_second_weight_convention():
     s = co.calculate_jaccard_scores(co.csr_from_edge_index(sub, n))
     want = np.clip((s - s.min()) / (s.max() - s.min()), 0.1, 1.0).astype(np.float32)
     assert bits_equal(w.cpu().numpy(), want)
+
+
+def test_self_loops_isolated_nodes_and_equal_degrees():
+    """Corner cases of the owner schedule: self loops (a pair with itself), ties in the degree order, isolated nodes."""
+    rng = np.random.default_rng(12)
+    n = 600
+    base = rmat_graph(n - 50, 4000, 9, seed=12)                       # nodes n-50..n-1 stay isolated
+    loops = rng.choice(n - 50, 80, replace=False)
+    ring = np.arange(200, 400)                                          # a ring: every node has the same degree
+    extra = np.vstack([np.r_[loops, ring, np.roll(ring, -1)], np.r_[loops, np.roll(ring, -1), ring]])
+    ei = np.concatenate([base, extra], axis=1)
+    keys = np.unique(ei[0] * n + ei[1])
+    ei = np.vstack([keys // n, keys % n])
+    for schedule in ("owner", "general"):
+        if schedule == "general":
+            import os
+            os.environ["GSP_INTERSECT"] = "general"
+        try:
+            sp = make_sparsifier(ei, n)
+            assert sp.graph.symmetric
+            csr = co.csr_from_edge_index(ei, n)
+            jac, inter = sp.graph.jaccard(return_counts=True)
+            want, want_inter = co.calculate_jaccard_scores(csr, return_counts=True)
+            assert np.array_equal(inter.cpu().numpy(), want_inter), schedule
+            assert bits_equal(jac.cpu().numpy(), want), schedule
+            assert bits_equal(sp.compute_scores("adamic_adar"), co.calculate_adamic_adar_scores(csr)), schedule
+        finally:
+            if schedule == "general":
+                del os.environ["GSP_INTERSECT"]
+    er = sp.compute_scores  # ApproxER with self loops: L folds a_ii into the diagonal (metrics.py:251-256)
+    sp.approx_er_options.update(k=16)
+    np.testing.assert_allclose(sp.compute_scores("approx_er"), co.calculate_approx_effective_resistance_scores(csr, k=16),
+                               rtol=1e-4, atol=1e-9)
