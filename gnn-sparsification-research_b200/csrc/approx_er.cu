@@ -227,16 +227,20 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
             const double dterm = __dmul_rn(diag[i], pi);
             double s = 0.0;
             bool placed = !single;                  // multi-segment rows: the diagonal is added by the combine kernel
+            int32_t jn[4];                          // ids of the next four-deep step, fetched one step ahead
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jn[u] = p0 + u < p1 ? __ldg(indices + p0 + u) : -1;
             for (int64_t t0 = p0; __any_sync(0xffffffffu, t0 < p1); t0 += 4) {   // row slots may differ in length
                 int32_t j[4];
                 double pj[4], a[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) j[u] = t0 + u < p1 ? __ldg(indices + t0 + u) : -1;
-#pragma unroll
                 for (int u = 0; u < 4; ++u) {
+                    j[u] = jn[u];
                     pj[u] = (lane_ok && j[u] >= 0) ? __ldg(p + (int64_t)j[u] * k + m.c) : 0.0;
                     a[u] = (data && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) jn[u] = t0 + 4 + u < p1 ? __ldg(indices + t0 + 4 + u) : -1;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (j[u] < 0) break;
