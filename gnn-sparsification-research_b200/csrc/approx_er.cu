@@ -273,34 +273,40 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
 // list of a row is read once per 64 columns instead of once per 32 and half as many load instructions are issued.
 // The neighbour ids of the next four-deep step are fetched while the current step's gathers are in flight (the first
 // version serialised "load ids -> gather p -> consume" and ran at 30 % occupancy / 12 % of the L2->SM path, ncu).
-template <bool kHasData>
+template <bool kHasData, bool kPacked>
 __global__ void __launch_bounds__(kThreads, 4)
 spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
                  const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
                  double* __restrict__ segpart, const int* __restrict__ active, double* __restrict__ partial) {
-    const int c = blockIdx.y * 64 + 2 * lane_id();
+    // k >= 64: one row per warp, 64-column strips. k in {2,4,...,32}: k/2 lanes per row, 64/k rows per warp.
+    const int lanes_per_row = kPacked ? k / 2 : kWarp;
+    const int rows_per_warp = kWarp / lanes_per_row;
+    const int sub = lane_id() / lanes_per_row;
+    const int c = blockIdx.y * 64 + 2 * (lane_id() % lanes_per_row);
     const bool any_active = active[c] | active[c + 1];
     double dot0 = 0.0, dot1 = 0.0;
     if (__any_sync(0xffffffffu, any_active)) {
         const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
-        for (int64_t it = warp; it < num_items; it += (int64_t)gridDim.x * kWarps) {
-            const int32_t i = items[it].row;
-            const int seg = items[it].seg;
+        for (int64_t base = warp * rows_per_warp; base < num_items; base += (int64_t)gridDim.x * kWarps * rows_per_warp) {
+            const int64_t it = base + sub;
+            const bool item_ok = it < num_items;
+            const int32_t i = item_ok ? items[it].row : 0;
+            const int seg = item_ok ? items[it].seg : 0;
             const int64_t row0 = indptr[i], row1 = indptr[i + 1];
-            const int64_t p0 = row0 + (int64_t)seg * kSeg;
-            const int64_t p1 = min(p0 + kSeg, row1);
+            const int64_t p0 = item_ok ? row0 + (int64_t)seg * kSeg : 0;
+            const int64_t p1 = item_ok ? min(p0 + kSeg, row1) : 0;
             const bool single = row1 - row0 <= kSeg;
             int32_t jn[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) jn[u] = p0 + u < p1 ? __ldg(indices + p0 + u) : -1;
             double2 pi = make_double2(0.0, 0.0);
-            if (single) pi = *reinterpret_cast<const double2*>(p + i * (int64_t)k + c);
+            if (single && item_ok) pi = *reinterpret_cast<const double2*>(p + i * (int64_t)k + c);
             const double di = diag[i];
             const double d0 = __dmul_rn(di, pi.x), d1 = __dmul_rn(di, pi.y);
             double s0 = 0.0, s1 = 0.0;
             bool placed = !single;
-            for (int64_t t0 = p0; t0 < p1; t0 += 4) {
+            for (int64_t t0 = p0; kPacked ? __any_sync(0xffffffffu, t0 < p1) : t0 < p1; t0 += 4) {   // packed row slots differ in length
                 int32_t j[4];
                 double2 pj[4];
                 double a[4];
@@ -330,19 +336,21 @@ spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int
                 }
             }
             if (!placed) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); }
-            if (single || seg == 0) {
-                *reinterpret_cast<double2*>(q + i * (int64_t)k + c) = make_double2(s0, s1);
-                if (single) {
-                    dot0 = __dadd_rn(dot0, __dmul_rn(pi.x, s0));
-                    dot1 = __dadd_rn(dot1, __dmul_rn(pi.y, s1));
+            if (item_ok) {
+                if (single || seg == 0) {
+                    *reinterpret_cast<double2*>(q + i * (int64_t)k + c) = make_double2(s0, s1);
+                    if (single) {
+                        dot0 = __dadd_rn(dot0, __dmul_rn(pi.x, s0));
+                        dot1 = __dadd_rn(dot1, __dmul_rn(pi.y, s1));
+                    }
+                } else {
+                    const int64_t slot = (i ? seg_incl[i - 1] : 0) - i + seg - 1;
+                    *reinterpret_cast<double2*>(segpart + slot * k + c) = make_double2(s0, s1);
                 }
-            } else {
-                const int64_t slot = (i ? seg_incl[i - 1] : 0) - i + seg - 1;
-                *reinterpret_cast<double2*>(segpart + slot * k + c) = make_double2(s0, s1);
             }
         }
     }
-    LaneMap m{c, 0, 1, kWarp, true};
+    LaneMap m{c, sub, rows_per_warp, lanes_per_row, true};
     block_column_partial(dot0, m, k, partial);
     m.c = c + 1;
     block_column_partial(dot1, m, k, partial);
@@ -588,17 +596,16 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
         GSP_CHECK_LAUNCH();
         direction_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, p.ptr, cg, it);
         GSP_CHECK_LAUNCH();
-        if (k % 64 == 0) {   // 64-column strips, two columns per lane
-            const dim3 grid64((unsigned)row_blocks, (unsigned)(k / 64));
-            if (g->data) {
-                spmm_dot2_kernel<true><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices,
-                                                                  g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,
-                                                                  partial.ptr);
-            } else {
-                spmm_dot2_kernel<false><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices,
-                                                                   nullptr, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,
-                                                                   partial.ptr);
-            }
+        const bool pow2_small = k >= 2 && k < 64 && (k & (k - 1)) == 0;
+        if (k % 64 == 0 || pow2_small) {   // two columns per lane: 64-column strips, or 64/k rows per warp when k < 64
+            const dim3 grid64((unsigned)row_blocks, (unsigned)(k >= 64 ? k / 64 : 1));
+#define GSP_SPMM2(HAS_DATA, PACKED)                                                                                          \
+    spmm_dot2_kernel<HAS_DATA, PACKED><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, \
+                                                                  g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,    \
+                                                                  partial.ptr)
+            if (g->data) { if (pow2_small) GSP_SPMM2(true, true); else GSP_SPMM2(true, false); }
+            else { if (pow2_small) GSP_SPMM2(false, true); else GSP_SPMM2(false, false); }
+#undef GSP_SPMM2
         } else {
             spmm_dot_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->data,
                                                        diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active, partial.ptr);
