@@ -153,6 +153,31 @@ def workload_name(args) -> str:
             f"{args.dim}-d fp32 features; Jaccard/AA/FeatCos scoring + top-{int(RETENTION * 100)}% select + compaction")
 
 
+def run_variants(dev):
+    """Degree-aware and sampled Jaccard sparsification through the public API on the ogbn-arxiv-shaped graph (BASELINE
+    config 3; the reference's own degree-aware loops are O(N*E) + O(E^2): 2.7 s at the Roman-empire shape, ~45 min here)."""
+    import gsr_b200
+    from gsr_b200.synthetic import SHAPES, rmat_graph_device
+
+    n3, e3, _, scale3, seed3 = SHAPES["arxiv"]
+    ei3 = rmat_graph_device(n3, e3, scale3, seed3, dev)
+    sp = gsr_b200.GraphSparsifier(gsr_b200.Data(edge_index=ei3, num_nodes=n3), str(dev))
+    sp.compute_scores("jaccard")
+    out = {"workload": f"arxiv-shaped R-MAT: {n3} nodes, {e3} directed edges; Jaccard scores cached, retention 0.5"}
+    for name, fn in (("threshold_ms", lambda: sp.sparsify("jaccard", 0.5, return_mask=True)),
+                     ("degree_aware_ms", lambda: sp.sparsify_degree_aware("jaccard", 0.5, return_mask=True)),
+                     ("sampled_numpy_choice_ms", lambda: sp.sparsify_sampled("jaccard", 0.5, return_mask=True)),
+                     ("sampled_device_ms", lambda: sp.sparsify_sampled("jaccard", 0.5, return_mask=True, method="device"))):
+        fn()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        out[name] = (time.perf_counter() - t0) / 3 * 1e3
+    return out
+
+
 def run_approx_er(args, dev, rank, world, group):
     """ApproxER-T sparsify (scores + top-50 % select + compaction) on the products-shaped R-MAT graph; projection columns
     are split over the ranks and the per-edge partial sums all-reduced (NCCL). Device Philox projection (throughput
@@ -385,6 +410,7 @@ def main() -> None:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
+    variants = run_variants(dev) if not args.no_e2e else None
 
     # ---- roofline (SURVEY §8d algorithmic bytes; peak = MEASURED_PEAKS.json hbm_gbs, fallback 6650 of B200_PROFILING.md)
     peak, peak_src = 6650.0, "fallback"
@@ -451,7 +477,7 @@ def main() -> None:
         "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": max_degree,
                    "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
                    "parallelism": f"x{world}: owner-sharded Jaccard/AA + reduce-scatter, edge-sliced FeatCos/select, CSR+features replicated"},
-        "per_method": per_kernel, "approx_er": approx_er, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "per_method": per_kernel, "approx_er": approx_er, "selection_variants": variants, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
