@@ -375,32 +375,62 @@ def main() -> None:
         del inter_t
         torch.cuda.synchronize(dev)
 
-    # ---- e2e through the reference-facing API, host inputs (rank-local replica; N>1 repeats it per rank) ----
+    # ---- e2e: host inputs (pinned), H2D and D2H inside the timed region ----------------------------------------------
+    # N = 1: the reference-facing API. N > 1: the same pipeline through the sharded entry points of the package
+    # (sharding.py), every rank uploading its replica of the inputs over its own PCIe link and reading back its slice.
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         ei_host = ei.cpu().pin_memory()
         x_host = x.cpu().pin_memory()
         h2d = ei_host.numel() * 8 + x_host.numel() * 4
         d2h = 0
         times = []
         for it in range(1 + args.e2e_steps):
-            torch.cuda.synchronize(dev)
+            barrier()
             t0 = time.perf_counter()
-            data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n).to(dev, non_blocking=True)   # H2D from pinned host memory
-            sp = gsr_b200.GraphSparsifier(data, str(dev))
-            d2h = 0
-            for m in METHODS:
-                s = sp.compute_scores(m)                                  # np.ndarray fp64 on host
-                out, msk = sp.sparsify(m, RETENTION, return_mask=True)    # Data (edge_index on device) + host bool mask
-                d2h += s.nbytes + msk.numel()
-                del out, msk
-            torch.cuda.synchronize(dev)
+            if world == 1:
+                data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n).to(dev, non_blocking=True)
+                sp = gsr_b200.GraphSparsifier(data, str(dev))
+                d2h = 0
+                for m in METHODS:
+                    s = sp.compute_scores(m)                                  # np.ndarray fp64 on host
+                    out, msk = sp.sparsify(m, RETENTION, return_mask=True)    # Data (edge_index on device) + host bool mask
+                    d2h += s.nbytes + msk.numel()
+                    del out, msk
+                del sp, data
+            else:
+                ei_d = ei_host.to(dev, non_blocking=True)
+                x_d = x_host.to(dev, non_blocking=True)
+                g2 = engine.DeviceGraph(ei_d, n)
+                nr = sharding.owner_node_ranges(g2, world)[rank]
+                d2h = 0
+                for m in METHODS:
+                    if m == "feature_cosine":
+                        sl = g2.feature_cosine(g2.normalize_features(x_d), e_lo, e_hi)
+                    else:
+                        sl = sharding.owner_sharded_scores(g2, m, group, nr, g2.aa_node_weights_numpy() if m == "adamic_adar" else None,
+                                                           scratch=full_scratch)[:local]
+                    mk = engine.select_mask_sharded(sl, num_keep, False, group)
+                    engine.compact_edges(ei_d[:, e_lo:e_hi].contiguous(), mk, kept_out.size(1), out=kept_out)
+                    s_host = torch.empty(local, dtype=torch.float64, pin_memory=True); s_host.copy_(sl, non_blocking=True)
+                    m_host = torch.empty(local, dtype=torch.uint8, pin_memory=True); m_host.copy_(mk, non_blocking=True)
+                    torch.cuda.synchronize(dev)
+                    d2h += s_host.numel() * 8 + m_host.numel()
+                del g2, ei_d, x_d
+            barrier()
             if it > 0:
                 times.append(time.perf_counter() - t0)
-            del sp, data
-        e2e = {"value": len(METHODS) * e / (sum(times) / len(times)), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": sum(times) / len(times) * 1e3,
-               "api": "data_host.to(cuda) -> GraphSparsifier(data, cuda) -> compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, return_mask=True) [host bool mask] for 3 metrics"}
+        t_e2e = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX, group=group)
+        api = ("data_host.to(cuda) -> GraphSparsifier(data, cuda) -> compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, "
+               "return_mask=True) [host bool mask] for 3 metrics") if world == 1 else (
+               "per rank: H2D replica -> DeviceGraph -> sharding.owner_sharded_scores / feature_cosine slice -> distributed select "
+               "-> compact -> D2H of the rank's score + mask slices, 3 metrics")
+        e2e = {"value": len(METHODS) * e / float(t_e2e), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e) * 1e3, "api": api,
+               "note": "bytes are per rank" if world > 1 else "single rank"}
 
     # ---- ApproxER sparsify ms (BASELINE config 4: products-shaped graph, JLT k = 64, CG rtol 1e-6, <= 500 iterations) ----
     approx_er = None
@@ -461,7 +491,7 @@ def main() -> None:
         pass
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
         adj, xs, es = cpu_sample_inputs()
         t0 = time.perf_counter()
         cpu_port_step(adj, xs, es)
