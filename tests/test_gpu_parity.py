@@ -552,3 +552,43 @@ def test_self_loops_isolated_nodes_and_equal_degrees():
     sp.approx_er_options.update(k=16)
     np.testing.assert_allclose(sp.compute_scores("approx_er"), co.calculate_approx_effective_resistance_scores(csr, k=16),
                                rtol=1e-4, atol=1e-9)
+
+
+def test_size_independent_properties_at_67m_edges():
+    """R-MAT scale 22 (4.2 M nodes, 67 M directed edges, hub degree ~10^5) generated on the device — far beyond what the
+    CPU oracle finishes — checked through invariants: mirrored positions carry identical bits, counts obey their bounds,
+    the three selections keep exactly int(E*r) edges, separate at the threshold and nest, shards reassemble."""
+    from gsr_b200.synthetic import rmat_graph_device
+
+    scale, n = 22, 1 << 22
+    e = n * 16
+    ei = rmat_graph_device(n, e, scale, seed=5, device=DEV)
+    gen = torch.Generator(device=DEV); gen.manual_seed(3)
+    x = torch.randn((n, 64), dtype=torch.float32, device=DEV, generator=gen)
+    sp = gsr_b200.GraphSparsifier(gsr_b200.Data(edge_index=ei, x=x, num_nodes=n), DEV)
+    g = sp.graph
+    assert g.nnz == e and g.symmetric and g.input_canonical and g.max_degree > 8192 * 4
+    jac, inter = g.jaccard(return_counts=True)
+    aa = g.adamic_adar(g.aa_node_weights_numpy())
+    fc = sp._device_scores("feature_cosine")
+    rev = torch.argsort(ei[1] * n + ei[0])                    # position of (v,u) for every canonical (u,v)
+    for s in (jac, aa, fc):
+        assert torch.equal(s[rev], s)
+    assert torch.equal(inter[rev], inter)
+    deg = g.degrees().long()
+    assert bool((inter.long() <= torch.minimum(deg[ei[0]], deg[ei[1]]) - 1).all()) and int(inter.min()) >= 0
+    assert bool(((aa > 0) == (inter > 0)).all())              # AA is a positive-weighted sum over the same common set
+    lo, hi = e // 3 + 17, (2 * e) // 3 + 5                     # an interior shard equals the slice of the full vector
+    assert torch.equal(g.jaccard(lo, hi), jac[lo:hi]) and torch.equal(g.feature_cosine(sp._xhat, lo, hi), fc[lo:hi])
+    prev = None
+    for rate in (0.2, 0.5, 0.9):
+        keep = int(e * rate)
+        m = engine.select_mask(fc, keep, False).bool()
+        assert int(m.sum()) == keep and float(fc[m].min()) >= float(fc[~m].max())
+        if prev is not None:
+            assert not bool((prev & ~m).any())
+        prev = m
+    mj = engine.select_mask(jac, e // 2, False).bool()          # heavy tie class (zeros) at the boundary or not: exact count
+    assert int(mj.sum()) == e // 2 and float(jac[mj].min()) >= float(jac[~mj].max())
+    kept, _, cnt = engine.compact_edges(ei, mj.to(torch.uint8), e // 2)
+    assert int(cnt) == e // 2 and torch.equal(kept, ei[:, mj])
