@@ -10,6 +10,7 @@ from .metrics import (
     calculate_feature_cosine_scores,
     calculate_jaccard_scores,
 )
+from .metric_backbone import compute_metric_backbone
 from .random import precompute_random_scores, random_sparsify
 
 __all__ = [
@@ -20,6 +21,7 @@ __all__ = [
     "calculate_effective_resistance_scores",
     "calculate_approx_effective_resistance_scores",
     "calculate_feature_cosine_scores",
+    "compute_metric_backbone",
     "precompute_random_scores",
     "random_sparsify",
 ]

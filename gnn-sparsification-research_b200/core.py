@@ -255,11 +255,14 @@ class GraphSparsifier:
         return sparse_data, w.to(self.device), _to_host(mask.view(torch.bool))
 
     def sparsify_metric_backbone(self, metric: str, epsilon: float = 1e-9):
-        """Metric-backbone sparsification (reference core.py:251-279) — APSP based, outside the B200 hot path."""
-        raise NotImplementedError(
-            "sparsify_metric_backbone (all-pairs shortest paths, reference metric_backbone.py) is outside the "
-            "edge-scoring hot path this engine accelerates (SURVEY §8f-3); `_scores_to_cost` is provided."
-        )
+        """Global metric backbone: keep edge (u,v) iff its cost <= shortest-path cost + epsilon (reference core.py:251-279).
+
+        Returns `(sparse_data_on_device, stats)`; the retention ratio follows from the graph, not from a parameter."""
+        from .metric_backbone import compute_metric_backbone
+
+        distances = self._scores_to_cost(self.compute_scores(metric), metric)
+        sparse_data, stats = compute_metric_backbone(self.data, distances, epsilon=epsilon, verbose=self.verbose)
+        return sparse_data.to(self.device), stats
 
     def sparsify_sampled(self, metric: str, retention_ratio: float, seed: int = 42, return_mask: bool = False,
                          method: str = "numpy"):

@@ -151,6 +151,16 @@ int gsp_approx_er_partial(const gsp_graph* g, const double* d_R, int64_t ldr, in
                           int32_t* d_iters, void* stream);
 int gsp_er_finalize(double* d_score, int64_t count, void* stream);
 
+/* ---- metric backbone ---------------------------------------------------------------
+ * Shortest-path lengths from the sources [src_begin, src_begin + src_count) to every node of a SYMMETRIC graph with
+ * non-negative edge lengths d_weights (fp64[nnz], canonical order) — replaces the all-pairs Dijkstra of reference
+ * metric_backbone.py:84-87. d_dist is fp64 [num_nodes, src_count] row-major (dist[v, s]); unreachable = +inf. In-place
+ * (min,+) relaxation sweeps until a sweep changes nothing (at most max_rounds; *rounds_out, host memory, receives the
+ * count). The fixpoint equals Dijkstra's lengths bit for bit (sums accumulate from the source; min is exact).
+ * Synchronises the stream every few sweeps. */
+int gsp_sssp_batch(const gsp_graph* g, const double* d_weights, int64_t src_begin, int32_t src_count, double* d_dist,
+                   int32_t max_rounds, int32_t* rounds_out, void* stream);
+
 /* ---- selection ---------------------------------------------------------------------------------
  * Radix-histogram select with stable (score, position) tie-breaking — replaces the full argsort of
  * reference core.py:232-240 (and :446-451 with an exclusion mask). Keys are fp64 scores mapped to

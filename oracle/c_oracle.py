@@ -64,6 +64,8 @@ def lib():
         L.gspo_approx_er.restype = C.c_int
         L.gspo_approx_er.argtypes = [C.c_int64, _i64p, _i32p, vp, C.c_int64, _f64p, C.c_int64, C.c_double,
                                      C.c_double, _f64p, vp, vp]
+        L.gspo_metric_backbone.restype = C.c_int
+        L.gspo_metric_backbone.argtypes = [C.c_int64, C.c_int64, _i64p, _i64p, _f64p, C.c_double, _u8p]
         _lib = L
     return _lib
 
@@ -212,3 +214,26 @@ def pairwise_sum(a: np.ndarray):
     if a.dtype == np.float32:
         return np.float32(lib().gspo_pairwise_sum_f32(a, len(a)))
     return np.float64(lib().gspo_pairwise_sum_f64(a.astype(np.float64), len(a)))
+
+
+def scores_to_cost(scores: np.ndarray, distance_metric: bool = False) -> np.ndarray:
+    """reference core.py:82-116 (similarity -> distance, d = 1/p - 1)."""
+    similarity = 1.0 / np.maximum(scores, 1e-10) if distance_metric else scores.copy()
+    top = similarity.max()
+    if top <= 0:
+        return np.ones_like(scores)
+    proximity = similarity / top
+    positive = proximity[proximity > 0]
+    floor = (positive.min() * 0.01) if len(positive) > 0 else 1e-6
+    proximity[proximity <= 0] = floor
+    return 1.0 / proximity - 1.0
+
+
+def metric_backbone_mask(edge_index: np.ndarray, num_nodes: int, edge_weights: np.ndarray, epsilon: float = 1e-9):
+    """reference metric_backbone.py:58-112: keep-mask over the edge_index columns."""
+    e = edge_index.shape[1]
+    mask = np.zeros(max(e, 1), np.uint8)
+    lib().gspo_metric_backbone(num_nodes, e, np.ascontiguousarray(edge_index[0], dtype=np.int64),
+                               np.ascontiguousarray(edge_index[1], dtype=np.int64),
+                               np.ascontiguousarray(edge_weights[:e], dtype=np.float64), float(epsilon), mask)
+    return mask[:e].astype(bool)

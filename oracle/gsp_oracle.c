@@ -416,3 +416,84 @@ GSPO_API int gspo_approx_er(int64_t n, const int64_t* indptr, const int32_t* ind
     if (!z_out) free(Z);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------
+ * Global metric backbone.  reference metric_backbone.py:58-112 (+ core.py:251-279).
+ *   G = undirected graph over the positions with u < v, weight = min over duplicates of that
+ *       orientation (the (v,u) positions do not contribute to G);
+ *   dist = all-pairs shortest path lengths (Dijkstra, fp64 sums accumulated from the source);
+ *   position idx is kept iff dist(u,v) is infinite or weights[idx] <= dist(u,v) + epsilon.
+ * Binary-heap Dijkstra from every source; mask has E entries.
+ * ---------------------------------------------------------------------------------- */
+typedef struct { double d; int32_t v; } gspo_hn;
+
+static void heap_push(gspo_hn* h, int64_t* sz, gspo_hn x) {
+    int64_t i = (*sz)++;
+    h[i] = x;
+    while (i > 0) {
+        int64_t p = (i - 1) / 2;
+        if (h[p].d <= h[i].d) break;
+        gspo_hn t = h[p]; h[p] = h[i]; h[i] = t; i = p;
+    }
+}
+static gspo_hn heap_pop(gspo_hn* h, int64_t* sz) {
+    gspo_hn top = h[0];
+    h[0] = h[--(*sz)];
+    int64_t i = 0;
+    for (;;) {
+        int64_t l = 2 * i + 1, r = l + 1, m = i;
+        if (l < *sz && h[l].d < h[m].d) m = l;
+        if (r < *sz && h[r].d < h[m].d) m = r;
+        if (m == i) break;
+        gspo_hn t = h[m]; h[m] = h[i]; h[i] = t; i = m;
+    }
+    return top;
+}
+
+GSPO_API int gspo_metric_backbone(int64_t n, int64_t E, const int64_t* row, const int64_t* col, const double* weights,
+                                  double epsilon, uint8_t* mask) {
+    /* undirected adjacency from the u < v positions, duplicates merged with min */
+    int64_t* ptr = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+    for (int64_t e = 0; e < E; ++e) if (row[e] < col[e]) { ptr[row[e] + 1]++; ptr[col[e] + 1]++; }
+    for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+    int64_t m2 = ptr[n];
+    int32_t* adj = (int32_t*)malloc((size_t)(m2 > 0 ? m2 : 1) * sizeof(int32_t));
+    double* aw = (double*)malloc((size_t)(m2 > 0 ? m2 : 1) * sizeof(double));
+    int64_t* cur = (int64_t*)malloc(((size_t)n + 1) * sizeof(int64_t));
+    memcpy(cur, ptr, ((size_t)n + 1) * sizeof(int64_t));
+    for (int64_t e = 0; e < E; ++e) if (row[e] < col[e]) {
+        adj[cur[row[e]]] = (int32_t)col[e]; aw[cur[row[e]]++] = weights[e];
+        adj[cur[col[e]]] = (int32_t)row[e]; aw[cur[col[e]]++] = weights[e];
+    }
+    double* dist = (double*)malloc((size_t)n * sizeof(double));
+    gspo_hn* heap = (gspo_hn*)malloc((size_t)(m2 + n + 1) * sizeof(gspo_hn));
+    /* positions grouped by source so each Dijkstra serves all of a node's out-positions */
+    int64_t* sptr = (int64_t*)calloc((size_t)n + 1, sizeof(int64_t));
+    for (int64_t e = 0; e < E; ++e) sptr[row[e] + 1]++;
+    for (int64_t i = 0; i < n; ++i) sptr[i + 1] += sptr[i];
+    int64_t* spos = (int64_t*)malloc((size_t)(E > 0 ? E : 1) * sizeof(int64_t));
+    memcpy(cur, sptr, ((size_t)n + 1) * sizeof(int64_t));
+    for (int64_t e = 0; e < E; ++e) spos[cur[row[e]]++] = e;
+    for (int64_t s = 0; s < n; ++s) {
+        if (sptr[s + 1] == sptr[s]) continue;
+        for (int64_t i = 0; i < n; ++i) dist[i] = INFINITY;
+        int64_t sz = 0;
+        dist[s] = 0.0;
+        heap_push(heap, &sz, (gspo_hn){0.0, (int32_t)s});
+        while (sz > 0) {
+            gspo_hn t = heap_pop(heap, &sz);
+            if (t.d > dist[t.v]) continue;
+            for (int64_t p = ptr[t.v]; p < ptr[t.v + 1]; ++p) {
+                double nd = t.d + aw[p];
+                if (nd < dist[adj[p]]) { dist[adj[p]] = nd; heap_push(heap, &sz, (gspo_hn){nd, adj[p]}); }
+            }
+        }
+        for (int64_t q = sptr[s]; q < sptr[s + 1]; ++q) {
+            int64_t e = spos[q];
+            double d = dist[col[e]];
+            mask[e] = (isinf(d) || weights[e] <= d + epsilon) ? 1 : 0;
+        }
+    }
+    free(spos); free(sptr); free(heap); free(dist); free(cur); free(aw); free(adj); free(ptr);
+    return 0;
+}

@@ -101,6 +101,10 @@ def main() -> None:
                     out[f"mask_dega2_{tag}"] = mask.numpy()
                     _, mask = sp.sparsify_sampled(m, r, seed=42, return_mask=True)
                     out[f"mask_samp_{tag}"] = mask.numpy()
+        if sp.adj.nnz == e and n <= 2000:        # global metric backbone (NetworkX APSP), metric_backbone.py:58-112
+            for m in ("jaccard", "adamic_adar"):
+                _, stats = sp.sparsify_metric_backbone(m)
+                out[f"mask_backbone_{m}"] = stats["keep_mask"]
         us, inv = ref.precompute_random_scores(data, seed=42)
         out["random_undirected_scores"], out["random_inverse_idx"] = us, inv.astype(np.int64)
         for r in RETENTIONS:

@@ -96,6 +96,10 @@ def test_golden_fixture(name):
                 if m == "jaccard":
                     _, mask = sp.sparsify_sampled(m, r, seed=42, return_mask=True)
                     assert np.array_equal(mask.numpy(), g[f"mask_samp_{tag}"]), "samp " + tag
+    for m in ("jaccard", "adamic_adar"):
+        if f"mask_backbone_{m}" in g:
+            _, stats = sp.sparsify_metric_backbone(m)
+            assert np.array_equal(stats["keep_mask"], g[f"mask_backbone_{m}"]), "backbone " + m
     us, inv = gsr_b200.precompute_random_scores(sp.data, seed=42)
     assert bits_equal(us, g["random_undirected_scores"]) and np.array_equal(inv, g["random_inverse_idx"])
     for r in RETENTIONS:
@@ -592,3 +596,55 @@ def test_size_independent_properties_at_67m_edges():
     assert int(mj.sum()) == e // 2 and float(jac[mj].min()) >= float(jac[~mj].max())
     kept, _, cnt = engine.compact_edges(ei, mj.to(torch.uint8), e // 2)
     assert int(cnt) == e // 2 and torch.equal(kept, ei[:, mj])
+
+
+# ----------------------------------------------------------------------------- metric backbone
+def _karate_unsorted():
+    g = load_golden("karate_unsorted")
+    return g["edge_index"], int(g["num_nodes"])
+
+
+def test_metric_backbone_reference_properties():
+    """reference tests/test_sparsification.py:44-112 re-run on the GPU implementation."""
+    ei, n = _karate_unsorted()
+    data = gsr_b200.Data(edge_index=torch.from_numpy(ei), num_nodes=n)
+    e = ei.shape[1]
+    sparse, stats = gsr_b200.compute_metric_backbone(data, np.ones(e), epsilon=1e-9, verbose=False)
+    assert sparse.edge_index.size(1) == e and stats["retention_ratio"] == 1.0          # uniform weights keep all
+    sp = gsr_b200.GraphSparsifier(data, "cpu")
+    costs = sp._scores_to_cost(sp.compute_scores("jaccard"), "jaccard")
+    sparse, stats = gsr_b200.compute_metric_backbone(data, costs, epsilon=1e-9, verbose=False)
+    assert stats["retention_ratio"] < 1.0 and sparse.edge_index.size(1) > 0
+    two_tri = torch.tensor([[0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5], [1, 2, 0, 2, 0, 1, 4, 5, 3, 5, 3, 4]])
+    sparse, _ = gsr_b200.compute_metric_backbone(gsr_b200.Data(edge_index=two_tri, num_nodes=6), np.ones(12), verbose=False)
+    assert sparse.edge_index.size(1) == 12                                             # disconnected components
+    single = gsr_b200.Data(edge_index=torch.tensor([[0, 1], [1, 0]]), num_nodes=2)
+    assert gsr_b200.compute_metric_backbone(single, np.array([1.0, 1.0]), verbose=False)[0].edge_index.size(1) == 2
+    tree = torch.tensor([[0, 0, 1, 1, 1, 2, 3, 4], [1, 2, 0, 3, 4, 0, 1, 1]])
+    assert gsr_b200.compute_metric_backbone(gsr_b200.Data(edge_index=tree, num_nodes=5), np.ones(8), verbose=False)[1][
+        "retention_ratio"] == 1.0
+
+
+@pytest.mark.parametrize("case", ["karate_unsorted", "rmat_1500", "chain", "hub"])
+def test_metric_backbone_against_oracle(case):
+    """Keep-mask equal to the oracle's Dijkstra (pinned to the live reference's NetworkX APSP in test_oracle_pin)."""
+    if case == "karate_unsorted":
+        ei, n = _karate_unsorted()
+    elif case == "rmat_1500":
+        ei, n = rmat_graph(1500, 9000, 11, seed=32), 1500
+    elif case == "chain":
+        ei, n = chain_with_shortcuts(3000, 200, seed=9), 3000           # long shortest paths: many relaxation sweeps
+    else:
+        ei, n = hub_graph(n=3000, hub_deg=1200, extra=9000, seed=6)
+    sp = make_sparsifier(ei, n, device=DEV)
+    for metric in ("jaccard", "adamic_adar"):
+        s = sp.compute_scores(metric)
+        cost = co.scores_to_cost(s)
+        assert bits_equal(sp._scores_to_cost(s, metric), cost)
+        want = co.metric_backbone_mask(ei, n, cost)
+        out, stats = sp.sparsify_metric_backbone(metric)
+        assert np.array_equal(stats["keep_mask"], want), (case, metric)
+        assert out.edge_index.is_cuda and np.array_equal(out.edge_index.cpu().numpy(), ei[:, want])
+        assert stats["retained_edges"] == int(want.sum()) and bits_equal(stats["sparse_weights"], cost[want])
+    assert labels.sparsify_by_composite(sp, "metric_backbone_jaccard", 0.5).edge_index.size(1) == int(
+        co.metric_backbone_mask(ei, n, co.scores_to_cost(sp.compute_scores("jaccard"))).sum())

@@ -37,6 +37,9 @@ def test_c_oracle_matches_golden(name):
         er = co.calculate_approx_effective_resistance_scores(csr, epsilon=float(g["er_epsilon"]))
         np.testing.assert_allclose(er, g["score_approx_er"], rtol=1e-4)      # north_star tolerance
         scores["approx_er"] = g["score_approx_er"]
+    for m in ("jaccard", "adamic_adar"):
+        if f"mask_backbone_{m}" in g:
+            assert np.array_equal(co.metric_backbone_mask(ei, n, co.scores_to_cost(g[f"score_{m}"])), g[f"mask_backbone_{m}"]), m
     for m, s in scores.items():
         if m == "degree":
             continue
@@ -153,3 +156,24 @@ def test_reference_property_tests_hold_for_oracle():
     star = sp.csr_matrix(np.array([[0, 1, 1, 1], [1, 0, 0, 0], [1, 0, 0, 0], [1, 0, 0, 0]]))
     assert np.all(np.isfinite(co.calculate_adamic_adar_scores(star)))
     assert np.all(co.calculate_approx_effective_resistance_scores(tri) > 0)
+
+
+@needs_ref
+@pytest.mark.parametrize("shape", [(34, None), (400, 3000), (1500, 9000)])
+def test_metric_backbone_oracle_matches_live_reference(shape):
+    """the oracle's Dijkstra backbone against the reference's NetworkX APSP (metric_backbone.py:58-112)."""
+    import torch
+    from gsr_b200.data import Data
+    from gsr_b200.synthetic import rmat_graph
+    from tests.helpers import load_golden
+
+    n, e = shape
+    ei = load_golden("karate_unsorted")["edge_index"] if e is None else rmat_graph(n, e, 11, seed=n)
+    ref = ref_loader.load(stable=True)
+    sp = ref.GraphSparsifier(Data(edge_index=torch.from_numpy(ei), num_nodes=n), "cpu")
+    for metric in ("jaccard", "adamic_adar"):
+        s = sp.compute_scores(metric)
+        cost = sp._scores_to_cost(s, metric)
+        assert bits_equal(co.scores_to_cost(s), cost)
+        _, stats = sp.sparsify_metric_backbone(metric)
+        assert np.array_equal(co.metric_backbone_mask(ei, n, cost), stats["keep_mask"]), metric
