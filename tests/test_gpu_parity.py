@@ -648,3 +648,25 @@ def test_metric_backbone_against_oracle(case):
         assert stats["retained_edges"] == int(want.sum()) and bits_equal(stats["sparse_weights"], cost[want])
     assert labels.sparsify_by_composite(sp, "metric_backbone_jaccard", 0.5).edge_index.size(1) == int(
         co.metric_backbone_mask(ei, n, co.scores_to_cost(sp.compute_scores("jaccard"))).sum())
+
+
+def test_select_three_million_scores_matches_stable_argsort():
+    """Multi-block tie ranking at 3 M scores (continuous, tie classes of n/3, 46 % exact zeros, values differing only in
+    the last mantissa bits) against NumPy's stable argsort."""
+    rng = np.random.default_rng(21)
+    n = 3_000_000
+    cases = {
+        "normal": rng.standard_normal(n),
+        "few_values": rng.integers(0, 3, n).astype(np.float64),                 # tie classes of n/3: list overflows
+        "half_zero": np.where(rng.random(n) < 0.46, 0.0, rng.random(n)),         # Jaccard-like: 46 % exact zeros
+        "tiny_range": 1.0 + rng.integers(0, 1 << 20, n).astype(np.float64) * 2.0 ** -52,   # differ only in the last bits
+    }
+    for name, scores in cases.items():
+        t = torch.from_numpy(scores).to(DEV)
+        order = np.argsort(scores, kind="stable")
+        for keep in (1, n // 7, n // 2, int(n * 0.9), n):
+            for kl in (False, True):
+                got = engine.select_mask(t, keep, kl).cpu().numpy().astype(bool)
+                want = np.zeros(n, bool)
+                want[order[:keep] if kl else order[n - keep:]] = True
+                assert np.array_equal(got, want), (name, keep, kl)
