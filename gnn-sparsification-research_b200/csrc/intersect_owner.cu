@@ -62,6 +62,7 @@ __device__ __forceinline__ bool hash_contains(const int32_t* slots, uint32_t mas
 // Keys that cannot be placed after kCuckooMaxKicks evictions go to a small stash that lookups scan only when it
 // is non-empty; if even the stash overflows the tile is rebuilt with the next pair of multipliers.
 constexpr int kJaccardDepth = 8;   // Jaccard streams long rows eight groups deep (counts need no ordering)
+constexpr int kQueueStride = 36;   // doubles per warp in the Adamic-Adar hit queue (32 + padding, 16-byte aligned)
 constexpr int kCuckooMaxKicks = 64;
 constexpr int kStashMax = 32;
 
@@ -268,7 +269,7 @@ __host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3
 __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ordered_sum) {
     // slots | base(int64) | acc(double) | len | cursor | rev | cnt | top | pad | per-warp hit queues (Adamic-Adar only)
     return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) +
-           (ordered_sum ? (size_t)(c.threads / kWarp) * kWarp * sizeof(double) : 0);
+           (ordered_sum ? (size_t)(c.threads / kWarp) * kQueueStride * sizeof(double) : 0);
 }
 
 // Process the part of row(w) below `cursor` that lies in the current tile's id range [lo_id, +inf), walking DOWN
@@ -283,11 +284,15 @@ template <int kMode>
 __device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queue, double& acc) {
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
     if (hits == 0) return;
-    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
-    __syncwarp();
     const int n = __popc(hits);
-#pragma unroll 4
-    for (int h = 0; h < n; ++h) acc = __dadd_rn(acc, queue[h]);
+    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
+    if (lane_id() < 3) queue[n + lane_id()] = 0.0;   // pad to a multiple of four: acc + 0.0 == acc (acc >= 0)
+    __syncwarp();
+    for (int h = 0; h < n; h += 4) {                 // two 16-byte broadcast loads + four ordered adds per step
+        const double2 a = *reinterpret_cast<const double2*>(queue + h);
+        const double2 b = *reinterpret_cast<const double2*>(queue + h + 2);
+        acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, a.x), a.y), b.x), b.y);
+    }
     __syncwarp();
 }
 
@@ -372,7 +377,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     int32_t* rev_s = cur_s + cls.chunk;                               // offset of o inside row(w)
     int32_t* cnt_s = rev_s + cls.chunk;
     int32_t* top_s = cnt_s + cls.chunk;                               // largest unprocessed id of row(w) (INT_MIN: none)
-    double* queue = reinterpret_cast<double*>(top_s + 2 * cls.chunk) + (threadIdx.x >> 5) * kWarp;   // valid when kMode == 1
+    double* queue = reinterpret_cast<double*>(top_s + 2 * cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode == 1
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
