@@ -103,9 +103,6 @@ int owner_costs(const Graph* g, double* cost, cudaStream_t s);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-// 128-bit read-only streaming load of four int32 (index lists are consumed once per intersection).
-__device__ __forceinline__ int4 ldg_int4(const int32_t* p) { return __ldg(reinterpret_cast<const int4*>(p)); }
-
 // Order-preserving map fp64 -> uint64 (ascending). -0.0 and +0.0 are made equal first because IEEE
 // comparison (what argsort uses) treats them as ties.
 __device__ __forceinline__ uint64_t ordered_key(double s) {
