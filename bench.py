@@ -281,6 +281,14 @@ def main() -> None:
     local = e_hi - e_lo
     node_range = sharding.owner_node_ranges(graph, world)[rank]
     full_scratch = torch.empty(slice_len * world, dtype=torch.float64, device=dev) if world > 1 else None
+    peer = None
+    if world > 1 and os.environ.get("GSP_BENCH_EXCHANGE", "p2p") == "p2p":
+        try:    # scores delivered by the scoring kernel itself through NVLink peer stores (symmetric memory)
+            peer = sharding.PeerScoreSlices(e, group, dev)
+        except Exception as exc:   # symmetric memory unavailable: NCCL reduce-scatter of the full vector
+            if rank == 0:
+                print(f"[bench] peer scatter unavailable ({type(exc).__name__}: {exc}); using reduce-scatter", file=sys.stderr)
+            peer = None
     num_keep = int(e * RETENTION)
 
     scores = torch.empty(slice_len if world > 1 else local, dtype=torch.float64, device=dev)
@@ -299,7 +307,11 @@ def main() -> None:
     def step(record: bool):
         for m in METHODS:
             ev[m][0].record()
-            if world > 1 and m != "feature_cosine":
+            if world > 1 and m != "feature_cosine" and peer is not None:
+                # owner-sharded, exchange fused into the scoring kernel: every score stored straight into its owner's slice
+                s_loc = sharding.owner_sharded_scores_p2p(graph, m, peer, node_range,
+                                                          aa_weights() if m == "adamic_adar" else None)[:local]
+            elif world > 1 and m != "feature_cosine":
                 # owner-sharded: each undirected pair evaluated on one rank, fp64 [E] reduce-scattered over NVLink
                 s_loc = sharding.owner_sharded_scores(graph, m, group, node_range, aa_weights() if m == "adamic_adar" else None,
                                                       scratch=full_scratch)[:local]
@@ -506,7 +518,7 @@ def main() -> None:
         "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
         "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": max_degree,
                    "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
-                   "parallelism": f"x{world}: owner-sharded Jaccard/AA + reduce-scatter, edge-sliced FeatCos/select, CSR+features replicated"},
+                   "parallelism": (f"x{world}: owner-sharded Jaccard/AA, exchange = " + ("peer stores from the scoring kernel (NVLink symmetric memory)" if peer is not None else "NCCL reduce-scatter") + ", edge-sliced FeatCos/select, CSR+features replicated")},
         "per_method": per_kernel, "approx_er": approx_er, "selection_variants": variants, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -288,6 +288,36 @@ GSP_API int gsp_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, i
     return owner_intersect_adamic_adar(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, d_score_full, s);
 }
 
+// Peer-scatter variants: the scoring kernel itself delivers every score to the rank that owns its position
+// (d_slices[k] = base of rank k's slice of `slice_len` positions, possibly peer memory mapped over NVLink).
+static int check_scatter(const Graph* g, int64_t node_begin, int64_t node_end, double* const* d_slices, int32_t world,
+                         int64_t slice_len) {
+    if (int rc = check_owned(g, node_begin, node_end, d_slices)) return rc;
+    GSP_REQUIRE(world >= 1 && slice_len >= 1 && (int64_t)world * slice_len >= g->nnz, "slices do not cover the positions");
+    return GSP_OK;
+}
+
+GSP_API int gsp_jaccard_owned_scatter(const gsp_graph* gg, int64_t node_begin, int64_t node_end, double* const* d_slices,
+                                      int32_t world, int64_t slice_len, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_scatter(g, node_begin, node_end, d_slices, world, slice_len)) return rc;
+    return owner_intersect_scatter(const_cast<Graph*>(g), 0, node_begin, node_end, nullptr, d_slices, slice_len, as_stream(stream));
+}
+
+GSP_API int gsp_adamic_adar_owned_scatter(const gsp_graph* gg, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                          double* const* d_slices, int32_t world, int64_t slice_len, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_scatter(g, node_begin, node_end, d_slices, world, slice_len)) return rc;
+    cudaStream_t s = as_stream(stream);
+    Scratch<double> w;
+    if (!d_node_w) {
+        GSP_CUDA_TRY(w.alloc(g->n, s));
+        if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
+        d_node_w = w.ptr;
+    }
+    return owner_intersect_scatter(const_cast<Graph*>(g), 1, node_begin, node_end, d_node_w, d_slices, slice_len, s);
+}
+
 GSP_API int gsp_owner_costs(const gsp_graph* gg, double* d_cost, void* stream) {
     GSP_REQUIRE(gg && d_cost, "NULL argument");
     return owner_costs(reinterpret_cast<const Graph*>(gg), d_cost, as_stream(stream));

@@ -128,6 +128,10 @@ struct RangeInfo {
     int32_t row_lo, row_hi;   // rows holding the first / last position of the range
     bool full;
     int32_t owner_lo, owner_hi;  // only pairs owned by nodes in [owner_lo, owner_hi) are evaluated (owner sharding)
+    // peer scatter (multi-GPU): position p goes to slices[p / slice_len][p % slice_len]; the pointers may be peer
+    // memory mapped over NVLink, so every score crosses the fabric exactly once, straight from the scoring kernel
+    double* const* slices;
+    int64_t slice_len;
 };
 
 // Stream row(w)[s, e) through the hash table. kMode 0: returns the number of hits. kMode 1: continues the
@@ -173,7 +177,7 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
     rev = __reduce_max_sync(0xffffffffu, rev);
 }
 
-template <int kMode>
+template <int kMode, bool kScatter>
 __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64_t p2, int d_o, int d_w, int count,
                                            double acc, int32_t* __restrict__ inter_out, double* __restrict__ score_out) {
     double score;
@@ -182,6 +186,15 @@ __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64
         score = uni > 0.0 ? __ddiv_rn((double)count, uni) : 0.0;
     } else {
         score = acc;
+    }
+    if (kScatter) {
+        const int64_t k1 = p1 / r.slice_len;
+        r.slices[k1][p1 - k1 * r.slice_len] = score;
+        if (p2 != p1) {
+            const int64_t k2 = p2 / r.slice_len;
+            r.slices[k2][p2 - k2 * r.slice_len] = score;
+        }
+        return;
     }
     if (p1 >= r.e_begin && p1 < r.e_end) {
         score_out[p1 - r.e_begin] = score;
@@ -194,7 +207,7 @@ __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64
 }
 
 // ---- level A: one warp per low-degree owner --------------------------------------------------------------
-template <int kMode>
+template <int kMode, bool kScatter>
 __global__ void __launch_bounds__(kAThreads)
 warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, RangeInfo r,
                   const double* __restrict__ node_w, int32_t* __restrict__ inter_out, double* __restrict__ score_out,
@@ -245,7 +258,7 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
                 int count = 0, rev = -1;
                 double acc = 0.0;
                 stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc, rev);
-                if (lane == 0 && rev >= 0) write_pair<kMode>(r, p1, b0 + rev, d_o, d_w, count, acc, inter_out, score_out);
+                if (lane == 0 && rev >= 0) write_pair<kMode, kScatter>(r, p1, b0 + rev, d_o, d_w, count, acc, inter_out, score_out);
             }
         }
     }
@@ -366,7 +379,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
     return cursor;
 }
 
-template <int kMode>
+template <int kMode, bool kScatter>
 __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, OwnerClass cls,
                                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, RangeInfo r,
                                  const double* __restrict__ node_w, int32_t* __restrict__ inter_out,
@@ -482,7 +495,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
         for (int i = threadIdx.x; i < nb; i += nthreads) {
             const int rev = rev_s[i];
             if (len_s[i] < 0 || rev < 0) continue;  // pair owned by the neighbour, or outside the range
-            write_pair<kMode>(r, a0 + j0 + i, base_s[i] + rev, d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
+            write_pair<kMode, kScatter>(r, a0 + j0 + i, base_s[i] + rev, d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
         }
     }
 }
@@ -562,26 +575,26 @@ OwnerClass hub_class_from_env(int& ctas_per_sm) {
     return c;
 }
 
-template <int kMode>
+template <int kMode, bool kScatter>
 int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, int ctas_per_sm, Graph* g, const RangeInfo& r,
                  const double* node_w, int32_t* inter, double* score, unsigned long long* counter, cudaStream_t s) {
     if (count <= 0) return GSP_OK;
     const size_t smem = owner_smem_bytes(cls, kMode == 1);
-    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode, kScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
-    cta_owner_kernel<kMode><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
+    cta_owner_kernel<kMode, kScatter><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
                                                                   score, counter);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
 
-template <int kMode>
+template <int kMode, bool kScatter>
 int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w, int32_t* inter,
-           double* score, cudaStream_t s) {
+           double* score, cudaStream_t s, double* const* slices = nullptr, int64_t slice_len = 0) {
     if (g->n == 0 || e_end == e_begin || owner_hi <= owner_lo) return GSP_OK;
     if (int rc = ensure_items(g, s)) return rc;
-    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi};
+    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi, slices, slice_len};
     if (!r.full) {
         Scratch<int32_t> rr;
         GSP_CUDA_TRY(rr.alloc(2, s));
@@ -600,12 +613,12 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     // hubs first: their long work items should not land in the tail
     int hub_ctas = 2;
     const OwnerClass hub = hub_class_from_env(hub_ctas);
-    if (int rc = launch_class<kMode>(hub, items + g->num_owner_items, g->num_hub_items, hub_ctas, g, r, node_w, inter, score,
+    if (int rc = launch_class<kMode, kScatter>(hub, items + g->num_owner_items, g->num_hub_items, hub_ctas, g, r, node_w, inter, score,
                                      counters.ptr, s)) return rc;
-    if (int rc = launch_class<kMode>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
+    if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
                                      counters.ptr + 1, s)) return rc;
     const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
-    warp_owner_kernel<kMode><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, r, node_w, inter,
+    warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, r, node_w, inter,
                                                                             score, counters.ptr + 2);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
@@ -635,12 +648,18 @@ __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr,
 
 int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
                             double* score, cudaStream_t s) {
-    return launch<0>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, s);
+    return launch<0, false>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, s);
 }
 
 int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
                                 const double* node_w, double* score, cudaStream_t s) {
-    return launch<1>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, s);
+    return launch<1, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, s);
+}
+
+int owner_intersect_scatter(Graph* g, int mode, int64_t owner_lo, int64_t owner_hi, const double* node_w,
+                            double* const* slices, int64_t slice_len, cudaStream_t s) {
+    return mode == 0 ? launch<0, true>(g, 0, g->nnz, owner_lo, owner_hi, nullptr, nullptr, nullptr, s, slices, slice_len)
+                     : launch<1, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, s, slices, slice_len);
 }
 
 int owner_costs(const Graph* g, double* cost, cudaStream_t s) {

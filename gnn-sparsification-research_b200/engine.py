@@ -153,6 +153,21 @@ class DeviceGraph:
                                                   self._stream()))
         return out
 
+    def owned_scatter(self, metric: str, node_begin: int, node_end: int, slices_dev_ptr: int, world: int, slice_len: int,
+                      node_weights: Optional[torch.Tensor] = None) -> None:
+        """Score the pairs owned by [node_begin, node_end) and store every score straight into the owning rank's slice;
+        `slices_dev_ptr` is the device address of an array of `world` slice base pointers (peer memory allowed)."""
+        sl = C.c_void_p(int(slices_dev_ptr))
+        with torch.cuda.device(self.device):
+            if metric == "jaccard":
+                check(self._lib.gsp_jaccard_owned_scatter(self._handle, int(node_begin), int(node_end), sl, int(world),
+                                                          int(slice_len), self._stream()))
+            elif metric == "adamic_adar":
+                check(self._lib.gsp_adamic_adar_owned_scatter(self._handle, ptr(node_weights), int(node_begin), int(node_end), sl,
+                                                              int(world), int(slice_len), self._stream()))
+            else:
+                raise ValueError(metric)
+
     def degree_product(self, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         score = self._empty(e - b, torch.float64) if out is None else out

@@ -88,6 +88,37 @@ def owner_sharded_scores(graph, metric: str, group, node_range: Tuple[int, int],
     return out
 
 
+class PeerScoreSlices:
+    """Per-rank fp64 score slices in NVLink-mapped symmetric memory (torch.distributed._symmetric_memory).
+
+    Every rank allocates its slice of `equal_slices(nnz, world)` positions, the rendezvous maps all slices into every
+    process, and the scoring kernel (`gsp_*_owned_scatter`) stores each score directly at its owner — the exchange is
+    fused into the compute kernel as plain peer stores, one crossing of the fabric per score (the reduce-scatter path moves
+    the full zero-padded vector from every rank). Raises if symmetric memory is unavailable; callers fall back to
+    `owner_sharded_scores`."""
+
+    def __init__(self, nnz: int, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.length, _ = equal_slices(nnz, self.world)
+        self.tensor = symm_mem.empty(self.length, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.slices_dev_ptr = int(self.handle.buffer_ptrs_dev)
+
+    def barrier(self):
+        self.handle.barrier()
+
+
+def owner_sharded_scores_p2p(graph, metric: str, peer: PeerScoreSlices, node_range: Tuple[int, int], node_weights=None):
+    """Owner-sharded Jaccard / Adamic-Adar with the exchange fused into the scoring kernel (peer stores over NVLink)."""
+    peer.barrier()                      # every rank is done reading the previous contents of its slice
+    graph.owned_scatter(metric, node_range[0], node_range[1], peer.slices_dev_ptr, peer.world, peer.length, node_weights)
+    peer.barrier()                      # all peers' stores into this rank's slice have landed
+    return peer.tensor
+
+
 def column_slice(k: int, rank: int, world: int) -> Tuple[int, int]:
     """Projection columns [lo, hi) of rank `rank` (ApproxER column sharding)."""
     return (k * rank) // world, (k * (rank + 1)) // world

@@ -113,6 +113,15 @@ int gsp_jaccard_owned(const gsp_graph* g, int64_t node_begin, int64_t node_end, 
 int gsp_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
                           double* d_score_full, void* stream);
 int gsp_owner_costs(const gsp_graph* g, double* d_cost, void* stream);
+/* Fused scoring + exchange: like the *_owned calls, but every score is stored by the scoring kernel directly into the
+ * slice of the rank that owns its position — d_slices is a DEVICE array of `world` pointers, d_slices[k] = base of rank
+ * k's fp64[slice_len] slice (position p lives at d_slices[p / slice_len][p % slice_len]); the pointers are typically
+ * peer allocations mapped over NVLink (e.g. torch symmetric memory), so each score crosses the fabric once and no
+ * reduce-scatter / zero-fill is needed. The caller brackets the call with a cross-rank barrier. */
+int gsp_jaccard_owned_scatter(const gsp_graph* g, int64_t node_begin, int64_t node_end, double* const* d_slices,
+                              int32_t world, int64_t slice_len, void* stream);
+int gsp_adamic_adar_owned_scatter(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                  double* const* d_slices, int32_t world, int64_t slice_len, void* stream);
 
 /* degree product — replaces reference core.py:167-172 (`degree` metric; raw-value row sums). */
 int gsp_degree_product(const gsp_graph* g, int64_t e_begin, int64_t e_end, double* d_score, void* stream);

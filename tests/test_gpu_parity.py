@@ -670,3 +670,25 @@ def test_select_three_million_scores_matches_stable_argsort():
                 want = np.zeros(n, bool)
                 want[order[:keep] if kl else order[n - keep:]] = True
                 assert np.array_equal(got, want), (name, keep, kl)
+
+
+def test_peer_scatter_scoring_with_emulated_ranks():
+    """gsp_*_owned_scatter: three node ranges ("ranks") store every score directly into the slice that owns its position
+    (three buffers on one device stand in for the NVLink-mapped peer slices); concatenated, the slices equal the
+    single-GPU vector."""
+    from gsr_b200 import sharding
+
+    ei, n = hub_graph(n=12000, hub_deg=9000, extra=30000, seed=8)
+    sp = make_sparsifier(ei, n)
+    g = sp.graph
+    w = g.aa_node_weights()
+    cuts = sharding.balanced_cuts(torch.cumsum(g.owner_costs(), 0), 3)
+    length, slices = sharding.equal_slices(g.nnz, 3)
+    for metric, full in (("jaccard", g.jaccard()), ("adamic_adar", g.adamic_adar(w))):
+        bufs = [torch.full((length,), -1.0, dtype=torch.float64, device=DEV) for _ in range(3)]
+        ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+        for r in range(3):
+            g.owned_scatter(metric, cuts[r], cuts[r + 1], ptrs.data_ptr(), 3, length, w if metric == "adamic_adar" else None)
+        got = torch.cat(bufs)[: g.nnz]
+        assert torch.equal(got, full), metric
+        assert bool((torch.cat(bufs)[g.nnz:] == -1.0).all())          # padding positions are never written
