@@ -342,6 +342,19 @@ def main() -> None:
             dist.barrier(group)
         torch.cuda.synchronize(dev)
 
+    if peer is not None:   # one-off cross-check of the fused peer-store exchange against the NCCL reduce-scatter path
+        ok = True
+        for m in ("jaccard", "adamic_adar"):
+            wts = aa_weights() if m == "adamic_adar" else None
+            a = sharding.owner_sharded_scores_p2p(graph, m, peer, node_range, wts)[:local].clone()
+            b = sharding.owner_sharded_scores(graph, m, group, node_range, wts, scratch=full_scratch)[:local]
+            ok = ok and bool(torch.equal(a, b))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
+        if int(flag) == 0:
+            if rank == 0:
+                print("[bench] peer-store exchange disagrees with reduce-scatter; falling back", file=sys.stderr)
+            peer = None
     for _ in range(max(args.warmup, 1)):
         step(False)
     # pass 1: per-kernel durations (CUDA events on the launching stream, one sync per method) for the roofline
