@@ -37,7 +37,8 @@ sys.path.insert(0, ROOT)
 
 METHODS = ("jaccard", "adamic_adar", "feature_cosine")
 RETENTION = 0.5
-CPU_SAMPLE = dict(scale=15, num_nodes=1 << 15, edges=(1 << 15) * 16, dim=128, seed=5)
+_CPU_SCALE = int(os.environ.get("GSP_BENCH_CPU_SCALE", "15"))     # R-MAT scale of the bounded CPU sample (tests shrink it)
+CPU_SAMPLE = dict(scale=_CPU_SCALE, num_nodes=1 << _CPU_SCALE, edges=(1 << _CPU_SCALE) * 16, dim=128, seed=5)
 
 
 # ------------------------------------------------------------------------------------------ clocks

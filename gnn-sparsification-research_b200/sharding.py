@@ -5,8 +5,10 @@ The path shards naturally:
   * scoring      every rank holds the replicated CSR (+ features). FeatCos / degree score one contiguous range of
                  canonical edges per rank with no communication. Jaccard / Adamic-Adar on a symmetric graph are
                  owner-sharded so no pair is evaluated twice: rank r evaluates the pairs owned by its node range
-                 (balanced by `gsp_owner_costs`), writes both directed positions into a zero-filled full-length
-                 buffer, and one reduce-scatter hands every rank its slice (asymmetric graphs: edge ranges);
+                 (balanced by `gsp_owner_costs`) and the exchange is fused into the scoring kernel: slices live in
+                 NVLink-mapped symmetric memory and every score is stored straight at the rank that owns its
+                 position (`PeerScoreSlices`, `owner_sharded_scores_p2p`); fallback: full-length zero-filled buffer +
+                 one reduce-scatter (`owner_sharded_scores`); asymmetric graphs: edge ranges;
   * selection    distributed radix select: per pass each rank histograms its slice, the 2048-bin histogram is
                  all-reduced (16 KB), every rank picks the same digit; one all-gather of per-rank tie counts
                  resolves the (score, position) boundary; each rank writes its mask slice;

@@ -102,3 +102,28 @@ def test_data_container_clone_is_deep():
     c = d.clone()
     c.edge_index[0, 0] = 7
     assert d.edge_index[0, 0] == 0 and c.num_nodes == 3
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times) prints one well-formed JSON line without a GPU."""
+    import json
+    import subprocess
+    import sys
+
+    env = dict(os.environ, GSP_BENCH_CPU_SCALE="9")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "edges/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["higher_is_better"] is True and line["metric"].startswith("edges scored/sec")
+
+
+def test_profiles_traffic_record_is_well_formed():
+    import json
+
+    t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    assert t["workload"] == {"scale": 24, "edge_factor": 16, "dim": 128, "n_gpus": 1}
+    for k in ("jaccard", "adamic_adar"):
+        assert t[k]["dram_bytes_per_launch"] > 1e11
