@@ -94,6 +94,8 @@ struct Graph {
 
 // graph.cu: CUB inclusive scan wrapper shared by the lazily built side structures
 int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s);
+int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
+                       cudaStream_t s);
 // intersect_owner.cu: fast path for symmetric graphs (each undirected pair evaluated once at its owner)
 int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
                             double* score, cudaStream_t s);

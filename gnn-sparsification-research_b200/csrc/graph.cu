@@ -386,6 +386,16 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
 
 int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s) { return inclusive_sum(in, out, count, s); }
 
+int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
+                       cudaStream_t s) {
+    size_t tmp_bytes = 0;
+    GSP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, count, 0, 32, s));
+    Scratch<char> tmp;
+    GSP_CUDA_TRY(tmp.alloc(tmp_bytes, s));
+    GSP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys_in, keys_out, vals_in, vals_out, count, 0, 32, s));
+    return GSP_OK;
+}
+
 }  // namespace gsp
 
 using namespace gsp;

@@ -524,6 +524,31 @@ __global__ void fill_items_kernel(int64_t n, const int64_t* __restrict__ indptr,
     }
 }
 
+// Sort key of a work item: the id of the first neighbour its chunk covers. Items sorted by it make the kernel sweep the id
+// space once with the chunks of ALL owners that cover an id window running at about the same time, so a neighbour row that
+// several owners stream is fetched from HBM once and then served by L2 (without the sort every use came from DRAM: ncu
+// measured 4*M bytes of DRAM reads).
+__global__ void item_keys_kernel(int64_t count, const OwnerItem* __restrict__ items, const int64_t* __restrict__ indptr,
+                                 const int32_t* __restrict__ indices, uint32_t* __restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        keys[i] = (uint32_t)indices[indptr[items[i].owner] + items[i].first];
+}
+
+int sort_items_by_window(OwnerItem* items, int64_t count, const Graph* g, cudaStream_t s) {
+    if (count <= 1) return GSP_OK;
+    static_assert(sizeof(OwnerItem) == sizeof(uint64_t), "items are sorted as 64-bit values");
+    Scratch<uint32_t> keys, keys_sorted;
+    Scratch<uint64_t> sorted;
+    GSP_CUDA_TRY(keys.alloc(count, s));
+    GSP_CUDA_TRY(keys_sorted.alloc(count, s));
+    GSP_CUDA_TRY(sorted.alloc(count, s));
+    item_keys_kernel<<<grid_for(count, 256), 256, 0, s>>>(count, items, g->indptr, g->indices, keys.ptr);
+    GSP_CHECK_LAUNCH();
+    if (int rc = sort_pairs_u32_u64(keys.ptr, keys_sorted.ptr, reinterpret_cast<const uint64_t*>(items), sorted.ptr, count, s)) return rc;
+    GSP_CUDA_TRY(cudaMemcpyAsync(items, sorted.ptr, (size_t)count * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    return GSP_OK;
+}
+
 __global__ void range_rows_kernel(const int32_t* __restrict__ rows, int64_t e_begin, int64_t e_end, int32_t* out) {
     out[0] = rows[e_begin];
     out[1] = rows[e_end - 1];
@@ -552,6 +577,11 @@ int ensure_items(Graph* g, cudaStream_t s) {
         GSP_CUDA_TRY(cudaMalloc(&items, (size_t)(totals[0] + totals[1]) * sizeof(OwnerItem)));
         fill_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, im.ptr, ih.ptr, items, items + totals[0]);
         GSP_CHECK_LAUNCH();
+        const char* order = getenv("GSP_ITEM_ORDER");   // "owner" keeps the owner-major order (for A/B measurements)
+        if (!(order && order[0] == 'o')) {
+            if (int rc = sort_items_by_window(items, totals[0], g, s)) { cudaFree(items); return rc; }
+            if (int rc = sort_items_by_window(items + totals[0], totals[1], g, s)) { cudaFree(items); return rc; }
+        }
         GSP_CUDA_TRY(cudaStreamSynchronize(s));
         g->owner_items = items;
     }
