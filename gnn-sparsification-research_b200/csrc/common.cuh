@@ -81,6 +81,7 @@ struct Graph {
     // transpose pattern (only when !symmetric): row v of A^T == column v of A
     int64_t* tptr = nullptr;
     int32_t* tidx = nullptr;
+    int32_t* rev_off = nullptr;  // [nnz] offset of u inside row(v) for position (u,v) (-1 when (v,u) is absent)
     // lazily built
     int32_t* und_id = nullptr;   // [nnz]
     void* seg_items = nullptr;   // row segments of the Laplacian SpMM (approx_er.cu)

@@ -154,7 +154,8 @@ __global__ void degree_stats_kernel(int64_t n, const int64_t* __restrict__ indpt
 
 // Pattern symmetry + undirected count + value flags in one pass over the canonical entries.
 __global__ void edge_stats_kernel(int64_t nnz, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                  const int32_t* __restrict__ rows, const double* __restrict__ data, GraphStats* st) {
+                                  const int32_t* __restrict__ rows, const double* __restrict__ data, GraphStats* st,
+                                  int32_t* __restrict__ rev_off) {
     unsigned long long und = 0;
     int asym = 0, non_unit = 0, zero = 0;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
@@ -166,7 +167,11 @@ __global__ void edge_stats_kernel(int64_t nnz, const int64_t* __restrict__ indpt
                 int64_t mid = (lo + hi) >> 1;
                 if (indices[mid] < u) lo = mid + 1; else hi = mid;
             }
-            if (!(lo < indptr[v + 1] && indices[lo] == u)) asym = 1;
+            const bool found = lo < indptr[v + 1] && indices[lo] == u;
+            if (!found) asym = 1;
+            rev_off[e] = found ? (int32_t)(lo - indptr[v]) : -1;   // offset of u inside row(v): the mirrored position
+        } else {
+            rev_off[e] = (int32_t)(e - indptr[u]);                 // a self loop mirrors onto itself
         }
         if (data) {
             double x = data[e];
@@ -232,6 +237,7 @@ void free_graph(Graph* g) {
     cudaFree(g->tptr);
     cudaFree(g->tidx);
     cudaFree(g->und_id);
+    cudaFree(g->rev_off);
     cudaFree(g->owner_items);
     cudaFree(g->seg_items);
     cudaFree(g->seg_incl);
@@ -338,8 +344,9 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
     degree_stats_kernel<<<grid_for(n, threads), threads, 0, s>>>(n, g->indptr, stats.ptr);
     GSP_CHECK_LAUNCH();
     if (g->nnz > 0) {
+        GSP_CUDA_TRY(cudaMalloc(&g->rev_off, (size_t)g->nnz * sizeof(int32_t)));
         edge_stats_kernel<<<grid_for(g->nnz, threads), threads, 0, s>>>(g->nnz, g->indptr, g->indices, g->rows, g->data,
-                                                                        stats.ptr);
+                                                                        stats.ptr, g->rev_off);
         GSP_CHECK_LAUNCH();
     }
     GraphStats hs;

@@ -6,9 +6,9 @@
 // pair {o, w} is evaluated ONCE, at its OWNER o = the endpoint with the larger degree (ties: smaller id):
 // the owner's neighbour set is put into a shared-memory hash table once and the (shorter) list of every
 // owned neighbour w is streamed through it with coalesced loads — sum over pairs of min(d) element tests,
-// one smem probe each. While row(w) streams by, the position of o inside it is seen as well, so the
-// score is written to both directed positions (o,w) and (w,o) (intersection, degrees and the
-// descending-id accumulation order are all symmetric in the pair).
+// one smem probe each. The score is written to both directed positions (o,w) and (w,o) — the mirrored position
+// comes from the reverse-offset array the graph build fills during its symmetry pass (intersection, degrees and
+// the descending-id accumulation order are all symmetric in the pair).
 //
 //   level A  rows with 1 <= deg <= 64: one warp per owner, 128-slot table per warp, neighbours in registers
 //   level B  rows with deg > 64: CTA per (owner, neighbour chunk). Two size classes of the same kernel:
@@ -135,21 +135,17 @@ struct RangeInfo {
 };
 
 // Stream row(w)[s, e) through the hash table. kMode 0: returns the number of hits. kMode 1: continues the
-// ordered fp64 accumulation (ids visited in descending order). rev receives the offset of `o` in row(w).
+// ordered fp64 accumulation (ids visited in descending order).
 template <int kMode>
 __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, int s, int e, const int32_t* slots,
                                            uint32_t mask, int shift, int32_t o, const double* __restrict__ node_w,
-                                           int& count, double& acc, int& rev) {
+                                           int& count, double& acc) {
     const int lane = lane_id();
     if (kMode == 0) {
         int c = 0;
         for (int base = s; base < e; base += kWarp) {
             const int i = base + lane;
-            if (i < e) {
-                const int32_t x = __ldg(row_w + i);
-                c += hash_contains(slots, mask, shift, x);
-                if (x == o) rev = i;
-            }
+            if (i < e) c += hash_contains(slots, mask, shift, __ldg(row_w + i));
         }
         count += __reduce_add_sync(0xffffffffu, c);
     } else {
@@ -160,7 +156,6 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
             if (i >= s) {
                 const int32_t x = __ldg(row_w + i);
                 hit = hash_contains(slots, mask, shift, x);
-                if (x == o) rev = i;
                 if (hit) {
                     const double w = __ldg(node_w + x);
                     term = __dmul_rn(w, w);
@@ -174,7 +169,6 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
             }
         }
     }
-    rev = __reduce_max_sync(0xffffffffu, rev);
 }
 
 template <int kMode, bool kScatter>
@@ -209,7 +203,8 @@ __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64
 // ---- level A: one warp per low-degree owner --------------------------------------------------------------
 template <int kMode, bool kScatter>
 __global__ void __launch_bounds__(kAThreads)
-warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, RangeInfo r,
+warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                  const int32_t* __restrict__ rev_off, RangeInfo r,
                   const double* __restrict__ node_w, int32_t* __restrict__ inter_out, double* __restrict__ score_out,
                   unsigned long long* counter) {
     __shared__ int32_t tables[kAWarps][kATableSlots];
@@ -255,10 +250,10 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
                     const bool w_in = b0 < r.e_end && b0 + d_w > r.e_begin;
                     if (!p1_in && !w_in) continue;
                 }
-                int count = 0, rev = -1;
+                int count = 0;
                 double acc = 0.0;
-                stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc, rev);
-                if (lane == 0 && rev >= 0) write_pair<kMode, kScatter>(r, p1, b0 + rev, d_o, d_w, count, acc, inter_out, score_out);
+                stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc);
+                if (lane == 0) write_pair<kMode, kScatter>(r, p1, b0 + __ldg(rev_off + p1), d_o, d_w, count, acc, inter_out, score_out);
             }
         }
     }
@@ -283,7 +278,7 @@ constexpr OwnerClass kHubClass{16384, 1024, 768};        // 64 KB tables + 36 KB
 __host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3; }
 
 __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ordered_sum) {
-    // slots | base(int64) | acc(double) | len | cursor | rev | cnt | top | pad | per-warp hit queues (Adamic-Adar only)
+    // slots | base(int64) | acc(double) | len | cursor | (spare) | cnt | top | pad | per-warp hit queues (Adamic-Adar only)
     return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) +
            (ordered_sum ? (size_t)(c.threads / kWarp) * kQueueStride * sizeof(double) : 0);
 }
@@ -314,8 +309,8 @@ __device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queu
 
 template <int kMode, bool kBounded>
 __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, int cursor, int32_t lo_id,
-                                           const Cuckoo& table, int32_t o, const double* __restrict__ node_w, double* queue,
-                                           int& count, double& acc, int& rev) {
+                                           const Cuckoo& table, const double* __restrict__ node_w, double* queue,
+                                           int& count, double& acc) {
     const int lane = lane_id();
     int c = 0;
     if (!kBounded) {
@@ -329,7 +324,6 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 for (int k = 0; k < D; ++k) {
                     if (k > 0 && top + lane - k * kWarp < 0) break;   // whole group below the row start (warp-uniform)
                     c += cuckoo_contains(table, x[k]);
-                    if (x[k] == o) rev = top - k * kWarp;
                 }
             } else {
                 // probe all four groups, then issue all weight gathers, then accumulate in order: the gather latency
@@ -337,10 +331,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 bool hit[D];
                 double w[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    hit[k] = cuckoo_contains(table, x[k]);
-                    if (x[k] == o) rev = top - k * kWarp;
-                }
+                for (int k = 0; k < D; ++k) hit[k] = cuckoo_contains(table, x[k]);
 #pragma unroll
                 for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
 #pragma unroll
@@ -361,7 +352,6 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 if (done || k >= groups) break;
                 const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
                 const bool hit = in_tile && cuckoo_contains(table, x[k]);
-                if (in_tile && x[k] == o) rev = top - k * kWarp;
                 if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, hit ? __ldg(node_w + x[k]) : 0.0, queue, acc);
                 const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
                 if (inside != 0xffffffffu) {           // ran off the tile (or the row): stop after this group
@@ -375,13 +365,13 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
         if (cursor < 0) cursor = 0;
     }
     if (kMode == 0) count += __reduce_add_sync(0xffffffffu, c);
-    rev = __reduce_max_sync(0xffffffffu, rev);
     return cursor;
 }
 
 template <int kMode, bool kScatter>
 __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, OwnerClass cls,
-                                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, RangeInfo r,
+                                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                 const int32_t* __restrict__ rev_off, RangeInfo r,
                                  const double* __restrict__ node_w, int32_t* __restrict__ inter_out,
                                  double* __restrict__ score_out, unsigned long long* counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -390,8 +380,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     double* acc_s = reinterpret_cast<double*>(base_s + cls.chunk);
     int32_t* len_s = reinterpret_cast<int32_t*>(acc_s + cls.chunk);   // row length, -1 = pair not evaluated here
     int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
-    int32_t* rev_s = cur_s + cls.chunk;                               // offset of o inside row(w)
-    int32_t* cnt_s = rev_s + cls.chunk;
+    int32_t* cnt_s = cur_s + 2 * cls.chunk;                           // (one spare int per neighbour keeps 8-byte alignment)
     int32_t* top_s = cnt_s + cls.chunk;                               // largest unprocessed id of row(w) (INT_MIN: none)
     double* queue = reinterpret_cast<double*>(top_s + 2 * cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode == 1
     __shared__ long long item_s;
@@ -435,7 +424,6 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
             len_s[i] = skip ? -1 : d_w;
             cur_s[i] = d_w;
             top_s[i] = (skip || d_w == 0) ? INT_MIN : __ldg(indices + b0 + d_w - 1);
-            rev_s[i] = -1;
             cnt_s[i] = 0;
             acc_s[i] = 0.0;
         }
@@ -474,15 +462,13 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                     // every neighbour row into pieces; most tiles miss most short rows)
                     if (top_s[i] < lo_id) continue;
                     const int cursor = cur_s[i];
-                    int count = 0, rev = -1;
+                    int count = 0;
                     double acc = kMode == 1 ? acc_s[i] : 0.0;
                     const int32_t* row_w = indices + base_s[i];
-                    const int new_cursor =
-                        t == 0 ? stream_down<kMode, false>(row_w, cursor, lo_id, table, o, node_w, queue, count, acc, rev)
-                               : stream_down<kMode, true>(row_w, cursor, lo_id, table, o, node_w, queue, count, acc, rev);
+                    const int new_cursor = t == 0 ? stream_down<kMode, false>(row_w, cursor, lo_id, table, node_w, queue, count, acc)
+                                                  : stream_down<kMode, true>(row_w, cursor, lo_id, table, node_w, queue, count, acc);
                     if (lane == 0) {
                         if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
-                        if (rev >= 0) rev_s[i] = rev;
                         if (t > 0) {   // the lowest tile consumes the rest of the row: nothing to carry over
                             cur_s[i] = new_cursor;
                             top_s[i] = new_cursor > 0 ? __ldg(row_w + new_cursor - 1) : INT_MIN;
@@ -493,9 +479,9 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
         }
         __syncthreads();
         for (int i = threadIdx.x; i < nb; i += nthreads) {
-            const int rev = rev_s[i];
-            if (len_s[i] < 0 || rev < 0) continue;  // pair owned by the neighbour, or outside the range
-            write_pair<kMode, kScatter>(r, a0 + j0 + i, base_s[i] + rev, d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
+            if (len_s[i] < 0) continue;  // pair owned by the neighbour, or outside the range
+            const int64_t p1 = a0 + j0 + i;
+            write_pair<kMode, kScatter>(r, p1, base_s[i] + __ldg(rev_off + p1), d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
         }
     }
 }
@@ -613,7 +599,7 @@ int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, i
     GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode, kScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
-    cta_owner_kernel<kMode, kScatter><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, r, node_w, inter,
+    cta_owner_kernel<kMode, kScatter><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, g->rev_off, r, node_w, inter,
                                                                   score, counter);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
@@ -648,7 +634,7 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
                                      counters.ptr + 1, s)) return rc;
     const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
-    warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, r, node_w, inter,
+    warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter,
                                                                             score, counters.ptr + 2);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
