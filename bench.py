@@ -411,11 +411,15 @@ def main() -> None:
         h2d = ei_host.numel() * 8 + x_host.numel() * 4
         d2h = 0
         times = []
+        h2d_ms = []
         for it in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
+            ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
             if world == 1:
                 data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n).to(dev, non_blocking=True)
+                ev1.record()
                 sp = gsr_b200.GraphSparsifier(data, str(dev))
                 d2h = 0
                 for m in METHODS:
@@ -427,6 +431,7 @@ def main() -> None:
             else:
                 ei_d = ei_host.to(dev, non_blocking=True)
                 x_d = x_host.to(dev, non_blocking=True)
+                ev1.record()
                 g2 = engine.DeviceGraph(ei_d, n)
                 nr = sharding.owner_node_ranges(g2, world)[rank]
                 d2h = 0
@@ -446,6 +451,7 @@ def main() -> None:
             barrier()
             if it > 0:
                 times.append(time.perf_counter() - t0)
+                h2d_ms.append(ev0.elapsed_time(ev1))   # the upload alone: tells a slow host link from a slow pipeline
         t_e2e = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
         if world > 1:
             import torch.distributed as dist
@@ -455,7 +461,9 @@ def main() -> None:
                "per rank: H2D replica -> DeviceGraph -> sharding.owner_sharded_scores / feature_cosine slice -> distributed select "
                "-> compact -> D2H of the rank's score + mask slices, 3 metrics")
         e2e = {"value": len(METHODS) * e / float(t_e2e), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e) * 1e3, "api": api,
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e) * 1e3,
+               "steps_ms": [round(t * 1e3, 1) for t in times], "h2d_ms": [round(t, 1) for t in h2d_ms],
+               "h2d_gbs": h2d / (sum(h2d_ms) / len(h2d_ms) * 1e-3) / 1e9, "api": api,
                "note": "bytes are per rank" if world > 1 else "single rank"}
 
     # ---- ApproxER sparsify ms (BASELINE config 4: products-shaped graph, JLT k = 64, CG rtol 1e-6, <= 500 iterations) ----

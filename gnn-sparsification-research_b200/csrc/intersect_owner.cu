@@ -65,7 +65,7 @@ __device__ __forceinline__ bool hash_contains(const int32_t* slots, uint32_t mas
 // Keys that cannot be placed after kCuckooMaxKicks evictions go to a small stash that lookups scan only when it
 // is non-empty; if even the stash overflows the tile is rebuilt with the next pair of multipliers.
 constexpr int kJaccardDepth = 8;   // Jaccard streams long rows eight groups deep (counts need no ordering)
-constexpr int kQueueStride = 36;   // doubles per warp in the Adamic-Adar hit queue (32 + padding, 16-byte aligned)
+constexpr int kQueueStride = 68;   // doubles per warp in the Adamic-Adar hit queue (two 32-id groups + padding, 16-byte aligned)
 constexpr int kCuckooMaxKicks = 64;
 constexpr int kStashMax = 32;
 
@@ -107,6 +107,23 @@ __device__ __forceinline__ bool cuckoo_contains(const Cuckoo& c, int32_t x) {
         for (int k = 0; k < c.stash_n; ++k) f |= c.stash[k] == x;
     }
     return f;
+}
+
+// Stash-free lookups for the main streaming loops (the caller checked stash_n == 0): two loads, two compares.
+__device__ __forceinline__ bool cuckoo_hit(const Cuckoo& c, int32_t x) {
+    const uint32_t ux = (uint32_t)x;
+    const int32_t a = lds_s32(c.t1 + (((ux * c.mul1) >> (c.shift - 2)) & ~3u));
+    const int32_t b = lds_s32(c.t2 + (((ux * c.mul2) >> (c.shift - 2)) & ~3u));
+    return (a == x) | (b == x);
+}
+
+// count += contains(x) as compare, compare-or, predicated add (the generic bool -> int path costs five instructions)
+__device__ __forceinline__ void cuckoo_count(const Cuckoo& c, int32_t x, int& count) {
+    const uint32_t ux = (uint32_t)x;
+    const int32_t a = lds_s32(c.t1 + (((ux * c.mul1) >> (c.shift - 2)) & ~3u));
+    const int32_t b = lds_s32(c.t2 + (((ux * c.mul2) >> (c.shift - 2)) & ~3u));
+    asm("{\n\t.reg .pred p, q;\n\tsetp.eq.s32 q, %1, %3;\n\tsetp.eq.or.s32 p, %2, %3, q;\n\t@p add.s32 %0, %0, 1;\n\t}"
+        : "+r"(count) : "r"(a), "r"(b), "r"(x));
 }
 
 // the pair {o, w} is evaluated at o unless w has the larger degree (ties: smaller id owns)
@@ -156,10 +173,7 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
             if (i >= s) {
                 const int32_t x = __ldg(row_w + i);
                 hit = hash_contains(slots, mask, shift, x);
-                if (hit) {
-                    const double w = __ldg(node_w + x);
-                    term = __dmul_rn(w, w);
-                }
+                if (hit) term = __ldg(node_w + x);   // node_w holds the squared weights
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
             while (hits) {
@@ -273,13 +287,13 @@ struct OwnerClass {
 };
 // slots = both cuckoo tables together; a tile holds at most kTileLoad * slots owner ids (load factor 0.375)
 constexpr int kMediumMaxDegree = 1536;
-constexpr OwnerClass kMediumClass{4096, 512, 256};       // 16 KB tables + 16 KB state: ~6 CTAs / SM
-constexpr OwnerClass kHubClass{16384, 1024, 768};        // 64 KB tables + 36 KB state: 2 CTAs / SM (40 regs x 1536 threads)
+constexpr OwnerClass kMediumClass{4096, 512, 256};       // 16 KB tables + 16 KB state + 4 KB queues: ~6 CTAs / SM
+constexpr OwnerClass kHubClass{16384, 1024, 768};        // 64 KB tables + 32 KB state + 13 KB queues: 2 CTAs / SM (40 regs x 1536 threads)
 __host__ __device__ constexpr int tile_ids_for(int slots) { return slots / 8 * 3; }
 
 __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ordered_sum) {
-    // slots | base(int64) | acc(double) | len | cursor | (spare) | cnt | top | pad | per-warp hit queues (Adamic-Adar only)
-    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) +
+    // slots | base(int64) | acc(double) | len | cursor | cnt | top | per-warp hit queues (Adamic-Adar only); chunk is even
+    return sizeof(int32_t) * (size_t)c.slots + (size_t)c.chunk * (8 + 8 + 4 + 4 + 4 + 4) +
            (ordered_sum ? (size_t)(c.threads / kWarp) * kQueueStride * sizeof(double) : 0);
 }
 
@@ -296,10 +310,31 @@ __device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queu
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
     if (hits == 0) return;
     const int n = __popc(hits);
-    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = __dmul_rn(w, w);   // lanes ascending == ids descending
+    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = w;   // lanes ascending == ids descending; w = weight squared
     if (lane_id() < 3) queue[n + lane_id()] = 0.0;   // pad to a multiple of four: acc + 0.0 == acc (acc >= 0)
     __syncwarp();
     for (int h = 0; h < n; h += 4) {                 // two 16-byte broadcast loads + four ordered adds per step
+        const double2 a = *reinterpret_cast<const double2*>(queue + h);
+        const double2 b = *reinterpret_cast<const double2*>(queue + h + 2);
+        acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, a.x), a.y), b.x), b.y);
+    }
+    __syncwarp();
+}
+
+// Two consecutive 32-id groups (group 0 holds the larger ids) through one queue pass: one padding store, one pair of
+// warp barriers and one replay loop for up to 64 hits.
+__device__ __forceinline__ void accumulate_hits2(bool hit0, double w0, bool hit1, double w1, double* queue, double& acc) {
+    const unsigned h0 = __ballot_sync(0xffffffffu, hit0);
+    const unsigned h1 = __ballot_sync(0xffffffffu, hit1);
+    if ((h0 | h1) == 0) return;
+    const unsigned lt = (1u << lane_id()) - 1u;
+    const int n0 = __popc(h0);
+    const int n = n0 + __popc(h1);
+    if (hit0) queue[__popc(h0 & lt)] = w0;
+    if (hit1) queue[n0 + __popc(h1 & lt)] = w1;
+    if (lane_id() < 3) queue[n + lane_id()] = 0.0;
+    __syncwarp();
+    for (int h = 0; h < n; h += 4) {
         const double2 a = *reinterpret_cast<const double2*>(queue + h);
         const double2 b = *reinterpret_cast<const double2*>(queue + h + 2);
         acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, a.x), a.y), b.x), b.y);
@@ -315,7 +350,30 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
     int c = 0;
     if (!kBounded) {
         constexpr int D = kMode == 0 ? kJaccardDepth : 4;   // 32-id groups fetched per round
-        for (int top = cursor - 1 - lane; top + lane >= 0; top -= D * kWarp) {
+        int top = cursor - 1 - lane;
+        if (table.stash_n == 0) {
+            // full rounds: every lane of every group is inside the row, so no bound tests, no sentinels, no stash scan
+            // (rows streamed by the CTA classes average several hundred ids: ~85 % of all groups take this loop)
+            for (int rounds = cursor / (D * kWarp); rounds > 0; --rounds, top -= D * kWarp) {
+                int32_t x[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = __ldg(row_w + top - k * kWarp);
+                if (kMode == 0) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) cuckoo_count(table, x[k], c);
+                } else {
+                    bool hit[D];
+                    double w[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) hit[k] = cuckoo_hit(table, x[k]);
+#pragma unroll
+                    for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc);
+                }
+            }
+        }
+        for (; top + lane >= 0; top -= D * kWarp) {
             int32_t x[D];
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = top - k * kWarp >= 0 ? __ldg(row_w + top - k * kWarp) : INT_MIN;
@@ -335,7 +393,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
 #pragma unroll
                 for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) accumulate_hits<kMode>(hit[k], w[k], queue, acc);
+                for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc);
             }
         }
         cursor = 0;
@@ -380,9 +438,9 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     double* acc_s = reinterpret_cast<double*>(base_s + cls.chunk);
     int32_t* len_s = reinterpret_cast<int32_t*>(acc_s + cls.chunk);   // row length, -1 = pair not evaluated here
     int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
-    int32_t* cnt_s = cur_s + 2 * cls.chunk;                           // (one spare int per neighbour keeps 8-byte alignment)
+    int32_t* cnt_s = cur_s + cls.chunk;
     int32_t* top_s = cnt_s + cls.chunk;                               // largest unprocessed id of row(w) (INT_MIN: none)
-    double* queue = reinterpret_cast<double*>(top_s + 2 * cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode == 1
+    double* queue = reinterpret_cast<double*>(top_s + cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode == 1
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
@@ -540,6 +598,13 @@ __global__ void range_rows_kernel(const int32_t* __restrict__ rows, int64_t e_be
     out[1] = rows[e_end - 1];
 }
 
+// w -> w * w once per call: the Adamic-Adar term of a common neighbour is the rounded square of its weight, so the
+// streaming kernels gather the term itself (same bits as squaring after the gather, one fp64 multiply less per hit)
+__global__ void square_weights_kernel(int64_t n, const double* __restrict__ w, double* __restrict__ w2) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        w2[i] = __dmul_rn(w[i], w[i]);
+}
+
 std::mutex g_items_mutex;
 
 int ensure_items(Graph* g, cudaStream_t s) {
@@ -621,6 +686,13 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
         GSP_CUDA_TRY(cudaStreamSynchronize(s));
         r.row_lo = h[0];
         r.row_hi = h[1];
+    }
+    Scratch<double> squared;
+    if (kMode == 1) {
+        GSP_CUDA_TRY(squared.alloc(g->n, s));
+        square_weights_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, node_w, squared.ptr);
+        GSP_CHECK_LAUNCH();
+        node_w = squared.ptr;
     }
     Scratch<unsigned long long> counters;
     GSP_CUDA_TRY(counters.alloc(3, s));
