@@ -6,7 +6,9 @@
 
 A *step* is one pass of the hot path over the whole synthetic graph: Jaccard, Adamic-Adar and feature-cosine
 scoring of every directed edge, each followed by global top-50 % selection (radix select) and edge_index
-compaction. Units per step = 3 x E edge scores.
+compaction. Units per step = 3 x E edge scores. Jaccard and Adamic-Adar walk the same neighbour lists, so the
+step takes both from ONE streaming pass (`gsp_jaccard_adamic_adar`, bit-identical to the separate calls;
+GSP_BENCH_FUSED=0 times two passes); `per_method` also lists each metric scored on its own.
 
   value  device-timed: graph CSR + features already resident in HBM, CUDA events around the K steps, max over ranks.
   e2e    the same step through the reference-facing API (`GraphSparsifier(data, ...)`, `compute_scores`, `sparsify`)
@@ -15,8 +17,8 @@ compaction. Units per step = 3 x E edge scores.
 
 N > 1 shards the canonical edge range over the ranks (CSR + features replicated, generated identically on every
 rank). FeatCos scores a contiguous edge slice per rank (no communication). Jaccard / Adamic-Adar are owner-sharded:
-every undirected pair is evaluated on exactly one rank and the fp64 score vector is reduce-scattered (NCCL over
-NVLink) so each rank ends up with its slice. Selection all-reduces 6 x 16 KB radix histograms. Fixed graph =>
+every undirected pair is evaluated on exactly one rank and every score is stored by the scoring kernel straight
+into the slice of the rank that owns its position (NVLink symmetric memory; NCCL reduce-scatter as the fallback). Selection all-reduces 6 x 16 KB radix histograms. Fixed graph =>
 "scaling": "strong".
 """
 from __future__ import annotations
@@ -281,11 +283,14 @@ def main() -> None:
     e_lo, e_hi = slices[rank]
     local = e_hi - e_lo
     node_range = sharding.owner_node_ranges(graph, world)[rank]
-    full_scratch = torch.empty(slice_len * world, dtype=torch.float64, device=dev) if world > 1 else None
-    peer = None
+    # Jaccard and Adamic-Adar come from ONE streaming pass (gsp_jaccard_adamic_adar*); GSP_BENCH_FUSED=0 times two passes
+    fused = os.environ.get("GSP_BENCH_FUSED", "1") != "0"
+    full_scratch = torch.empty(slice_len * world * (2 if fused else 1), dtype=torch.float64, device=dev) if world > 1 else None
+    peer = peer_j = None
     if world > 1 and os.environ.get("GSP_BENCH_EXCHANGE", "p2p") == "p2p":
         try:    # scores delivered by the scoring kernel itself through NVLink peer stores (symmetric memory)
             peer = sharding.PeerScoreSlices(e, group, dev)
+            peer_j = sharding.PeerScoreSlices(e, group, dev) if fused else None
         except Exception as exc:   # symmetric memory unavailable: NCCL reduce-scatter of the full vector
             if rank == 0:
                 print(f"[bench] peer scatter unavailable ({type(exc).__name__}: {exc}); using reduce-scatter", file=sys.stderr)
@@ -293,49 +298,69 @@ def main() -> None:
     num_keep = int(e * RETENTION)
 
     scores = torch.empty(slice_len if world > 1 else local, dtype=torch.float64, device=dev)
+    scores_j = torch.empty(local, dtype=torch.float64, device=dev) if fused and world == 1 else None
     mask = torch.empty(local, dtype=torch.uint8, device=dev)
     ei_local = ei[:, e_lo:e_hi].contiguous() if world > 1 else ei
     kept_out = torch.empty((2, num_keep if world == 1 else local), dtype=torch.int64, device=dev)
-    ev = {m: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for m in METHODS}
-    ev_sel = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kernel_ms = {m: 0.0 for m in METHODS}
+    BOTH = "jaccard+adamic_adar"
+    phases = ([BOTH] if fused else ["jaccard", "adamic_adar"]) + ["feature_cosine"]     # scoring launches of one step
+    # CUDA events around every scoring call and every select+compact of every TIMED step (recorded on the launching stream
+    # inside the timed region, read after its closing synchronize: no host sync between the steps)
+    def new_events():
+        return ({m: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for m in phases},
+                [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in METHODS])
+    step_events = [new_events() for _ in range(args.steps)]
+    spare_events = new_events()
+    kernel_ms = {m: 0.0 for m in phases}
     kernel_ms["select+compact"] = 0.0
+    kernel_ms_steps = {m: [] for m in kernel_ms}
 
     def aa_weights():
         # per-degree constant table (NumPy expression, built once per graph) gathered per node on the device
         return graph.aa_node_weights_numpy()
 
-    def step(record: bool):
-        for m in METHODS:
+    def score_single(m):
+        """One metric's scores for this rank's slice of canonical positions (separate pass per metric)."""
+        if world > 1 and m != "feature_cosine" and peer is not None:
+            # owner-sharded, exchange fused into the scoring kernel: every score stored straight into its owner's slice
+            return sharding.owner_sharded_scores_p2p(graph, m, peer, node_range, aa_weights() if m == "adamic_adar" else None)[:local]
+        if world > 1 and m != "feature_cosine":
+            # owner-sharded: each undirected pair evaluated on one rank, fp64 [E] reduce-scattered over NVLink
+            return sharding.owner_sharded_scores(graph, m, group, node_range, aa_weights() if m == "adamic_adar" else None,
+                                                 scratch=full_scratch)[:local]
+        if m == "jaccard":
+            return graph.jaccard(e_lo, e_hi, out=scores[:local])
+        if m == "adamic_adar":
+            return graph.adamic_adar(aa_weights(), e_lo, e_hi, out=scores[:local])
+        xhat = graph.normalize_features(x)
+        return graph.feature_cosine(xhat, e_lo, e_hi, out=scores[:local])
+
+    def score_both():
+        """(jaccard, adamic_adar) slices from one streaming pass over the neighbour lists."""
+        if world > 1 and peer is not None:
+            j, a = sharding.owner_sharded_jaccard_adamic_adar_p2p(graph, peer_j, peer, node_range, aa_weights())
+            return j[:local], a[:local]
+        if world > 1:
+            j, a = sharding.owner_sharded_jaccard_adamic_adar(graph, group, node_range, aa_weights(), scratch=full_scratch)
+            return j[:local], a[:local]
+        return graph.jaccard_adamic_adar(aa_weights(), e_lo, e_hi, out_jaccard=scores_j, out_adamic_adar=scores[:local])
+
+    def step(k):
+        ev, ev_sel = step_events[k] if k is not None else spare_events
+        sel = 0
+        for m in phases:
             ev[m][0].record()
-            if world > 1 and m != "feature_cosine" and peer is not None:
-                # owner-sharded, exchange fused into the scoring kernel: every score stored straight into its owner's slice
-                s_loc = sharding.owner_sharded_scores_p2p(graph, m, peer, node_range,
-                                                          aa_weights() if m == "adamic_adar" else None)[:local]
-            elif world > 1 and m != "feature_cosine":
-                # owner-sharded: each undirected pair evaluated on one rank, fp64 [E] reduce-scattered over NVLink
-                s_loc = sharding.owner_sharded_scores(graph, m, group, node_range, aa_weights() if m == "adamic_adar" else None,
-                                                      scratch=full_scratch)[:local]
-            elif m == "jaccard":
-                s_loc = graph.jaccard(e_lo, e_hi, out=scores[:local])
-            elif m == "adamic_adar":
-                s_loc = graph.adamic_adar(aa_weights(), e_lo, e_hi, out=scores[:local])
-            else:
-                xhat = graph.normalize_features(x)
-                s_loc = graph.feature_cosine(xhat, e_lo, e_hi, out=scores[:local])
-                del xhat
+            outs = score_both() if m == BOTH else (score_single(m),)
             ev[m][1].record()
-            ev_sel[0].record()
-            if world > 1:
-                engine.select_mask_sharded(s_loc, num_keep, False, group, out=mask)
-            else:
-                engine.select_mask(s_loc, num_keep, False, out=mask)
-            engine.compact_edges(ei_local, mask, kept_out.size(1), out=kept_out)   # true count stays on the device
-            ev_sel[1].record()
-            if record:
-                torch.cuda.synchronize(dev)
-                kernel_ms[m] += ev[m][0].elapsed_time(ev[m][1])
-                kernel_ms["select+compact"] += ev_sel[0].elapsed_time(ev_sel[1])
+            for s_loc in outs:                     # every method: top-50 % select + compaction of its own scores
+                ev_sel[sel][0].record()
+                if world > 1:
+                    engine.select_mask_sharded(s_loc, num_keep, False, group, out=mask)
+                else:
+                    engine.select_mask(s_loc, num_keep, False, out=mask)
+                engine.compact_edges(ei_local, mask, kept_out.size(1), out=kept_out)   # true count stays on the device
+                ev_sel[sel][1].record()
+                sel += 1
 
     def barrier():
         if world > 1:
@@ -350,6 +375,9 @@ def main() -> None:
             a = sharding.owner_sharded_scores_p2p(graph, m, peer, node_range, wts)[:local].clone()
             b = sharding.owner_sharded_scores(graph, m, group, node_range, wts, scratch=full_scratch)[:local]
             ok = ok and bool(torch.equal(a, b))
+            if fused:   # the fused pass + fused exchange against the same reference
+                fj, fa = score_both()
+                ok = ok and bool(torch.equal(fj if m == "jaccard" else fa, b))
         flag = torch.tensor([1 if ok else 0], device=dev)
         torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=group)
         if int(flag) == 0:
@@ -357,12 +385,21 @@ def main() -> None:
                 print("[bench] peer-store exchange disagrees with reduce-scatter; falling back", file=sys.stderr)
             peer = None
     for _ in range(max(args.warmup, 1)):
-        step(False)
-    # pass 1: per-kernel durations (CUDA events on the launching stream, one sync per method) for the roofline
-    barrier()
-    for _ in range(args.steps):
-        step(True)
-    # pass 2: the reported number — K steps back to back, no host sync inside, max over ranks
+        step(None)
+    # per-method durations of the separate passes (reported in per_method; not part of the step when the pass is fused)
+    single_ms = {}
+    if fused:
+        for m in ("jaccard", "adamic_adar"):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            score_single(m)
+            barrier()
+            a.record()
+            for _ in range(args.steps):
+                score_single(m)
+            b.record()
+            barrier()
+            single_ms[m] = a.elapsed_time(b)
+    # the reported number — K steps back to back, no host sync inside, max over ranks
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -370,20 +407,27 @@ def main() -> None:
     launches0 = lib.gsp_launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for _ in range(args.steps):
-        step(False)
+    for k in range(args.steps):
+        step(k)
     t_end.record()
     barrier()
+    for ev, ev_sel in step_events:    # per-call durations of the timed steps themselves (roofline, per_method)
+        for m in phases:
+            kernel_ms_steps[m].append(ev[m][0].elapsed_time(ev[m][1]))
+        kernel_ms_steps["select+compact"].append(sum(a.elapsed_time(b) for a, b in ev_sel))
+    for m in kernel_ms:
+        kernel_ms[m] = sum(kernel_ms_steps[m])
     launches = lib.gsp_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX, group=group)
-        for k in kernel_ms:
-            t = torch.tensor([kernel_ms[k]], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            kernel_ms[k] = float(t)
+        for d in (kernel_ms, single_ms):
+            for k in d:
+                t = torch.tensor([d[k]], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+                d[k] = float(t)
     ms_per_step = float(elapsed_ms) / args.steps
     value = len(METHODS) * e / (ms_per_step * 1e-3)
 
@@ -421,6 +465,8 @@ def main() -> None:
                 data = gsr_b200.Data(edge_index=ei_host, x=x_host, num_nodes=n).to(dev, non_blocking=True)
                 ev1.record()
                 sp = gsr_b200.GraphSparsifier(data, str(dev))
+                if fused:
+                    sp.prefetch_scores(METHODS)
                 d2h = 0
                 for m in METHODS:
                     s = sp.compute_scores(m)                                  # np.ndarray fp64 on host
@@ -435,9 +481,13 @@ def main() -> None:
                 g2 = engine.DeviceGraph(ei_d, n)
                 nr = sharding.owner_node_ranges(g2, world)[rank]
                 d2h = 0
+                both = (sharding.owner_sharded_jaccard_adamic_adar(g2, group, nr, g2.aa_node_weights_numpy(), scratch=full_scratch)
+                        if fused else None)
                 for m in METHODS:
                     if m == "feature_cosine":
                         sl = g2.feature_cosine(g2.normalize_features(x_d), e_lo, e_hi)
+                    elif both is not None:
+                        sl = both[0 if m == "jaccard" else 1][:local]
                     else:
                         sl = sharding.owner_sharded_scores(g2, m, group, nr, g2.aa_node_weights_numpy() if m == "adamic_adar" else None,
                                                            scratch=full_scratch)[:local]
@@ -456,7 +506,7 @@ def main() -> None:
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX, group=group)
-        api = ("data_host.to(cuda) -> GraphSparsifier(data, cuda) -> compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, "
+        api = ("data_host.to(cuda) -> GraphSparsifier(data, cuda) -> " + ("prefetch_scores(methods) -> " if fused else "") + "compute_scores(m) [host fp64 ndarray] + sparsify(m, 0.5, "
                "return_mask=True) [host bool mask] for 3 metrics") if world == 1 else (
                "per rank: H2D replica -> DeviceGraph -> sharding.owner_sharded_scores / feature_cosine slice -> distributed select "
                "-> compact -> D2H of the rank's score + mask slices, 3 metrics")
@@ -490,21 +540,26 @@ def main() -> None:
     alg_bytes = {
         "jaccard": (4.0 * sum_min + 28.0 * e) * frac_edges,
         "adamic_adar": (4.0 * sum_min + 28.0 * e + 8.0 * common) * frac_edges,
+        BOTH: (4.0 * sum_min + 36.0 * e + 8.0 * common) * frac_edges,    # the Adamic-Adar pass + the second fp64 output
         "feature_cosine": (4.0 * args.dim * e + 4.0 * e + 8.0 * e) * frac_edges + 12.0 * args.dim * n,
         "select+compact": (8.0 * local * 8 + local) + 17.0 * local + 16.0 * num_keep / world,
     }
     survey_bytes = {"jaccard": (4.0 * s2 + 20.0 * e) * frac_edges, "adamic_adar": (4.0 * s2 + 20.0 * e + 8.0 * 2 * common) * frac_edges}
     per_kernel = {}
-    for k, ms in kernel_ms.items():
+    for k, ms in list(kernel_ms.items()) + list(single_ms.items()):
         avg = ms / args.steps
         gbs = alg_bytes[k] / (avg * 1e-3) / 1e9 if avg > 0 else 0.0
         per_kernel[k] = {"ms": avg, "alg_gb": alg_bytes[k] / 1e9, "achieved_gbs": gbs, "frac": gbs / peak,
-                         "edges_per_s": (local / (avg * 1e-3)) if k != "select+compact" else None}
+                         "edges_per_s": ((2 if k == BOTH else 1) * local / (avg * 1e-3)) if k != "select+compact" else None,
+                         "in_step": k in kernel_ms}
+        if k in kernel_ms_steps:
+            per_kernel[k]["ms_steps"] = [round(v, 3) for v in kernel_ms_steps[k]]
         if k in survey_bytes:
             per_kernel[k]["survey_formula_gb"] = survey_bytes[k] / 1e9
             per_kernel[k]["survey_formula_frac"] = survey_bytes[k] / (avg * 1e-3) / 1e9 / peak
-    dominant = max(METHODS, key=lambda m: kernel_ms[m])
-    roofline = {"bound": "hbm", "kernel": {"jaccard": "cta_owner_kernel<0> (+warp_owner_kernel<0>)",
+    dominant = max(phases, key=lambda m: kernel_ms[m])
+    roofline = {"bound": "hbm", "kernel": {BOTH: "cta_owner_kernel<2> (+warp_owner_kernel<2>): Jaccard and Adamic-Adar in one pass",
+                                            "jaccard": "cta_owner_kernel<0> (+warp_owner_kernel<0>)",
                                             "adamic_adar": "cta_owner_kernel<1> (+warp_owner_kernel<1>)",
                                             "feature_cosine": "featcos_kernel<float>"}[dominant],
                 "achieved": per_kernel[dominant]["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -540,6 +595,8 @@ def main() -> None:
         "dtype": "int32 indices / f64 scores / f32 features", "data": "synthetic",
         "config": {"workload": workload_name(args), "nodes": n, "directed_edges": e, "max_degree": max_degree,
                    "sum_degree_sq": s2, "sum_pairs_min_degree": sum_min, "common_neighbour_pairs": common, "retention": RETENTION, "l2": "inputs_larger_than_L2",
+                   "scoring_passes": ("Jaccard + Adamic-Adar from one streaming pass (gsp_jaccard_adamic_adar), FeatCos" if fused
+                                      else "one pass per method"),
                    "parallelism": (f"x{world}: owner-sharded Jaccard/AA, exchange = " + ("peer stores from the scoring kernel (NVLink symmetric memory)" if peer is not None else "NCCL reduce-scatter") + ", edge-sliced FeatCos/select, CSR+features replicated")},
         "per_method": per_kernel, "approx_er": approx_er, "selection_variants": variants, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks,

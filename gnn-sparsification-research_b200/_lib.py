@@ -50,13 +50,16 @@ PROTOTYPES = {
     "gsp_graph_undirected_ids": (_INT, [_P, _P, _P]),
     "gsp_jaccard": (_INT, [_P, _I64, _I64, _P, _P, _P]),
     "gsp_adamic_adar": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "gsp_jaccard_adamic_adar": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _P]),
     "gsp_aa_node_weights": (_INT, [_P, _P, _P]),
     "gsp_aa_node_weights_from_table": (_INT, [_P, _P, _I64, _P, _P]),
     "gsp_jaccard_owned": (_INT, [_P, _I64, _I64, _P, _P, _P]),
     "gsp_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P]),
+    "gsp_jaccard_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P, _P]),
     "gsp_owner_costs": (_INT, [_P, _P, _P]),
     "gsp_jaccard_owned_scatter": (_INT, [_P, _I64, _I64, _P, _I32, _I64, _P]),
     "gsp_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _I32, _I64, _P]),
+    "gsp_jaccard_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _P, _I32, _I64, _P]),
     "gsp_degree_product": (_INT, [_P, _I64, _I64, _P, _P]),
     "gsp_featcos_normalize_f32": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
     "gsp_featcos_f32": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),

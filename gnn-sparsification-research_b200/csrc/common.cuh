@@ -103,8 +103,10 @@ int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t ow
 int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
                                 const double* node_w, double* score, cudaStream_t s);
 int owner_costs(const Graph* g, double* cost, cudaStream_t s);
+int owner_intersect_both(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w,
+                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s);
 int owner_intersect_scatter(Graph* g, int mode, int64_t owner_lo, int64_t owner_hi, const double* node_w,
-                            double* const* slices, int64_t slice_len, cudaStream_t s);
+                            double* const* slices, int64_t slice_len, cudaStream_t s, double* const* slices2 = nullptr);
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

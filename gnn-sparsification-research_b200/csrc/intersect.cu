@@ -239,6 +239,28 @@ GSP_API int gsp_adamic_adar(const gsp_graph* gg, const double* d_node_w, int64_t
     return launch_intersect<1>(g, e_begin, e_end, d_node_w, nullptr, d_score, s);
 }
 
+GSP_API int gsp_jaccard_adamic_adar(const gsp_graph* gg, const double* d_node_w, int64_t e_begin, int64_t e_end,
+                                    int32_t* d_inter, double* d_jaccard, double* d_adamic_adar, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_range(g, e_begin, e_end)) return rc;
+    if (e_end == e_begin) return GSP_OK;
+    GSP_REQUIRE(d_jaccard != nullptr && d_adamic_adar != nullptr, "output is NULL");
+    if (!use_owner_path(g)) {
+        // asymmetric pattern (Jaccard intersects row(u) with col(v), Adamic-Adar with row(v)) or the forced general
+        // schedule: two passes
+        if (int rc = gsp_jaccard(gg, e_begin, e_end, d_inter, d_jaccard, stream)) return rc;
+        return gsp_adamic_adar(gg, d_node_w, e_begin, e_end, d_adamic_adar, stream);
+    }
+    cudaStream_t s = as_stream(stream);
+    Scratch<double> w;
+    if (!d_node_w) {
+        GSP_CUDA_TRY(w.alloc(g->n, s));
+        if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
+        d_node_w = w.ptr;
+    }
+    return owner_intersect_both(const_cast<Graph*>(g), e_begin, e_end, 0, g->n, d_node_w, d_inter, d_jaccard, d_adamic_adar, s);
+}
+
 GSP_API int gsp_degree_product(const gsp_graph* gg, int64_t e_begin, int64_t e_end, double* d_score, void* stream) {
     const Graph* g = reinterpret_cast<const Graph*>(gg);
     if (int rc = check_range(g, e_begin, e_end)) return rc;
@@ -288,6 +310,22 @@ GSP_API int gsp_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, i
     return owner_intersect_adamic_adar(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, d_score_full, s);
 }
 
+GSP_API int gsp_jaccard_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                          double* d_jaccard_full, double* d_adamic_adar_full, void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_owned(g, node_begin, node_end, d_jaccard_full)) return rc;
+    if (int rc = check_owned(g, node_begin, node_end, d_adamic_adar_full)) return rc;
+    cudaStream_t s = as_stream(stream);
+    Scratch<double> w;
+    if (!d_node_w) {
+        GSP_CUDA_TRY(w.alloc(g->n, s));
+        if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
+        d_node_w = w.ptr;
+    }
+    return owner_intersect_both(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, nullptr, d_jaccard_full,
+                                d_adamic_adar_full, s);
+}
+
 // Peer-scatter variants: the scoring kernel itself delivers every score to the rank that owns its position
 // (d_slices[k] = base of rank k's slice of `slice_len` positions, possibly peer memory mapped over NVLink).
 static int check_scatter(const Graph* g, int64_t node_begin, int64_t node_end, double* const* d_slices, int32_t world,
@@ -316,6 +354,24 @@ GSP_API int gsp_adamic_adar_owned_scatter(const gsp_graph* gg, const double* d_n
         d_node_w = w.ptr;
     }
     return owner_intersect_scatter(const_cast<Graph*>(g), 1, node_begin, node_end, d_node_w, d_slices, slice_len, s);
+}
+
+GSP_API int gsp_jaccard_adamic_adar_owned_scatter(const gsp_graph* gg, const double* d_node_w, int64_t node_begin,
+                                                  int64_t node_end, double* const* d_jaccard_slices,
+                                                  double* const* d_adamic_adar_slices, int32_t world, int64_t slice_len,
+                                                  void* stream) {
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    if (int rc = check_scatter(g, node_begin, node_end, d_jaccard_slices, world, slice_len)) return rc;
+    if (int rc = check_scatter(g, node_begin, node_end, d_adamic_adar_slices, world, slice_len)) return rc;
+    cudaStream_t s = as_stream(stream);
+    Scratch<double> w;
+    if (!d_node_w) {
+        GSP_CUDA_TRY(w.alloc(g->n, s));
+        if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
+        d_node_w = w.ptr;
+    }
+    return owner_intersect_scatter(const_cast<Graph*>(g), 2, node_begin, node_end, d_node_w, d_adamic_adar_slices, slice_len, s,
+                                   d_jaccard_slices);
 }
 
 GSP_API int gsp_owner_costs(const gsp_graph* gg, double* d_cost, void* stream) {

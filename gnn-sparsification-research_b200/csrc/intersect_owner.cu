@@ -149,10 +149,12 @@ struct RangeInfo {
     // memory mapped over NVLink, so every score crosses the fabric exactly once, straight from the scoring kernel
     double* const* slices;
     int64_t slice_len;
+    double* const* slices2;   // Jaccard slices of the fused Jaccard + Adamic-Adar pass (kMode 2)
 };
 
 // Stream row(w)[s, e) through the hash table. kMode 0: returns the number of hits. kMode 1: continues the
-// ordered fp64 accumulation (ids visited in descending order).
+// ordered fp64 accumulation (ids visited in descending order). kMode 2: both (the fused pass: the hit ballots the
+// ordered sum needs anyway also give the count).
 template <int kMode>
 __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, int s, int e, const int32_t* slots,
                                            uint32_t mask, int shift, int32_t o, const double* __restrict__ node_w,
@@ -176,6 +178,7 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
                 if (hit) term = __ldg(node_w + x);   // node_w holds the squared weights
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if (kMode == 2) count += __popc(hits);
             while (hits) {
                 const int src = __ffs(hits) - 1;
                 acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, term, src));
@@ -185,32 +188,38 @@ __device__ __forceinline__ void stream_row(const int32_t* __restrict__ row_w, in
     }
 }
 
+// score_out receives the Jaccard score (kMode 0) or the Adamic-Adar sum (kMode 1, 2); jaccard_out the Jaccard score of
+// the fused pass (kMode 2).
 template <int kMode, bool kScatter>
 __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64_t p2, int d_o, int d_w, int count,
-                                           double acc, int32_t* __restrict__ inter_out, double* __restrict__ score_out) {
-    double score;
-    if (kMode == 0) {
+                                           double acc, int32_t* __restrict__ inter_out, double* __restrict__ score_out,
+                                           double* __restrict__ jaccard_out) {
+    double jac = 0.0;
+    if (kMode != 1) {
         const double uni = (double)d_o + (double)d_w - (double)count;
-        score = uni > 0.0 ? __ddiv_rn((double)count, uni) : 0.0;
-    } else {
-        score = acc;
+        jac = uni > 0.0 ? __ddiv_rn((double)count, uni) : 0.0;
     }
+    const double score = kMode == 0 ? jac : acc;
     if (kScatter) {
         const int64_t k1 = p1 / r.slice_len;
         r.slices[k1][p1 - k1 * r.slice_len] = score;
+        if (kMode == 2) r.slices2[k1][p1 - k1 * r.slice_len] = jac;
         if (p2 != p1) {
             const int64_t k2 = p2 / r.slice_len;
             r.slices[k2][p2 - k2 * r.slice_len] = score;
+            if (kMode == 2) r.slices2[k2][p2 - k2 * r.slice_len] = jac;
         }
         return;
     }
     if (p1 >= r.e_begin && p1 < r.e_end) {
         score_out[p1 - r.e_begin] = score;
-        if (kMode == 0 && inter_out) inter_out[p1 - r.e_begin] = count;
+        if (kMode == 2) jaccard_out[p1 - r.e_begin] = jac;
+        if (kMode != 1 && inter_out) inter_out[p1 - r.e_begin] = count;
     }
     if (p2 != p1 && p2 >= r.e_begin && p2 < r.e_end) {
         score_out[p2 - r.e_begin] = score;
-        if (kMode == 0 && inter_out) inter_out[p2 - r.e_begin] = count;
+        if (kMode == 2) jaccard_out[p2 - r.e_begin] = jac;
+        if (kMode != 1 && inter_out) inter_out[p2 - r.e_begin] = count;
     }
 }
 
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kAThreads)
 warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                   const int32_t* __restrict__ rev_off, RangeInfo r,
                   const double* __restrict__ node_w, int32_t* __restrict__ inter_out, double* __restrict__ score_out,
-                  unsigned long long* counter) {
+                  double* __restrict__ jaccard_out, unsigned long long* counter) {
     __shared__ int32_t tables[kAWarps][kATableSlots];
     const int lane = lane_id();
     int32_t* slots = tables[threadIdx.x >> 5];
@@ -267,7 +276,8 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
                 int count = 0;
                 double acc = 0.0;
                 stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc);
-                if (lane == 0) write_pair<kMode, kScatter>(r, p1, b0 + __ldg(rev_off + p1), d_o, d_w, count, acc, inter_out, score_out);
+                if (lane == 0)
+                    write_pair<kMode, kScatter>(r, p1, b0 + __ldg(rev_off + p1), d_o, d_w, count, acc, inter_out, score_out, jaccard_out);
             }
         }
     }
@@ -306,10 +316,11 @@ __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ord
 // descending-id order, then every lane replays the queue (broadcast loads) with the sequential fp64 adds the
 // reference's SpGEMM performs. ~3 issue slots per hit instead of ~8 for a ballot/shuffle loop.
 template <int kMode>
-__device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queue, double& acc) {
+__device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queue, double& acc, int& nhits) {
     const unsigned hits = __ballot_sync(0xffffffffu, hit);
     if (hits == 0) return;
     const int n = __popc(hits);
+    nhits += n;   // warp-uniform; dead code unless the fused pass reads it
     if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = w;   // lanes ascending == ids descending; w = weight squared
     if (lane_id() < 3) queue[n + lane_id()] = 0.0;   // pad to a multiple of four: acc + 0.0 == acc (acc >= 0)
     __syncwarp();
@@ -323,13 +334,15 @@ __device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queu
 
 // Two consecutive 32-id groups (group 0 holds the larger ids) through one queue pass: one padding store, one pair of
 // warp barriers and one replay loop for up to 64 hits.
-__device__ __forceinline__ void accumulate_hits2(bool hit0, double w0, bool hit1, double w1, double* queue, double& acc) {
+__device__ __forceinline__ void accumulate_hits2(bool hit0, double w0, bool hit1, double w1, double* queue, double& acc,
+                                                 int& nhits) {
     const unsigned h0 = __ballot_sync(0xffffffffu, hit0);
     const unsigned h1 = __ballot_sync(0xffffffffu, hit1);
     if ((h0 | h1) == 0) return;
     const unsigned lt = (1u << lane_id()) - 1u;
     const int n0 = __popc(h0);
     const int n = n0 + __popc(h1);
+    nhits += n;
     if (hit0) queue[__popc(h0 & lt)] = w0;
     if (hit1) queue[n0 + __popc(h1 & lt)] = w1;
     if (lane_id() < 3) queue[n + lane_id()] = 0.0;
@@ -347,7 +360,8 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                                            const Cuckoo& table, const double* __restrict__ node_w, double* queue,
                                            int& count, double& acc) {
     const int lane = lane_id();
-    int c = 0;
+    int c = 0;    // per-lane hits (kMode 0)
+    int nh = 0;   // warp-uniform hits (kMode 2)
     if (!kBounded) {
         constexpr int D = kMode == 0 ? kJaccardDepth : 4;   // 32-id groups fetched per round
         int top = cursor - 1 - lane;
@@ -369,7 +383,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
 #pragma unroll
                     for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
 #pragma unroll
-                    for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc);
+                    for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc, nh);
                 }
             }
         }
@@ -393,7 +407,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
 #pragma unroll
                 for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
 #pragma unroll
-                for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc);
+                for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc, nh);
             }
         }
         cursor = 0;
@@ -410,7 +424,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 if (done || k >= groups) break;
                 const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
                 const bool hit = in_tile && cuckoo_contains(table, x[k]);
-                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, hit ? __ldg(node_w + x[k]) : 0.0, queue, acc);
+                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, hit ? __ldg(node_w + x[k]) : 0.0, queue, acc, nh);
                 const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
                 if (inside != 0xffffffffu) {           // ran off the tile (or the row): stop after this group
                     done = true;
@@ -423,6 +437,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
         if (cursor < 0) cursor = 0;
     }
     if (kMode == 0) count += __reduce_add_sync(0xffffffffu, c);
+    if (kMode == 2) count += nh;
     return cursor;
 }
 
@@ -431,7 +446,8 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                  const int32_t* __restrict__ rev_off, RangeInfo r,
                                  const double* __restrict__ node_w, int32_t* __restrict__ inter_out,
-                                 double* __restrict__ score_out, unsigned long long* counter) {
+                                 double* __restrict__ score_out, double* __restrict__ jaccard_out,
+                                 unsigned long long* counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* slots = reinterpret_cast<int32_t*>(smem_raw);
     long long* base_s = reinterpret_cast<long long*>(smem_raw + sizeof(int32_t) * (size_t)cls.slots);
@@ -440,7 +456,7 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
     int32_t* cur_s = len_s + cls.chunk;                               // unprocessed prefix of row(w)
     int32_t* cnt_s = cur_s + cls.chunk;
     int32_t* top_s = cnt_s + cls.chunk;                               // largest unprocessed id of row(w) (INT_MIN: none)
-    double* queue = reinterpret_cast<double*>(top_s + cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode == 1
+    double* queue = reinterpret_cast<double*>(top_s + cls.chunk) + (threadIdx.x >> 5) * kQueueStride;   // valid when kMode != 0
     __shared__ long long item_s;
     __shared__ int next_s;
     const int lane = lane_id();
@@ -521,12 +537,13 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                     if (top_s[i] < lo_id) continue;
                     const int cursor = cur_s[i];
                     int count = 0;
-                    double acc = kMode == 1 ? acc_s[i] : 0.0;
+                    double acc = kMode != 0 ? acc_s[i] : 0.0;
                     const int32_t* row_w = indices + base_s[i];
                     const int new_cursor = t == 0 ? stream_down<kMode, false>(row_w, cursor, lo_id, table, node_w, queue, count, acc)
                                                   : stream_down<kMode, true>(row_w, cursor, lo_id, table, node_w, queue, count, acc);
                     if (lane == 0) {
-                        if (kMode == 0) cnt_s[i] += count; else acc_s[i] = acc;
+                        if (kMode != 1) cnt_s[i] += count;
+                        if (kMode != 0) acc_s[i] = acc;
                         if (t > 0) {   // the lowest tile consumes the rest of the row: nothing to carry over
                             cur_s[i] = new_cursor;
                             top_s[i] = new_cursor > 0 ? __ldg(row_w + new_cursor - 1) : INT_MIN;
@@ -539,7 +556,8 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
         for (int i = threadIdx.x; i < nb; i += nthreads) {
             if (len_s[i] < 0) continue;  // pair owned by the neighbour, or outside the range
             const int64_t p1 = a0 + j0 + i;
-            write_pair<kMode, kScatter>(r, p1, base_s[i] + __ldg(rev_off + p1), d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out);
+            write_pair<kMode, kScatter>(r, p1, base_s[i] + __ldg(rev_off + p1), d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out,
+                                        jaccard_out);
         }
     }
 }
@@ -658,24 +676,27 @@ OwnerClass hub_class_from_env(int& ctas_per_sm) {
 
 template <int kMode, bool kScatter>
 int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, int ctas_per_sm, Graph* g, const RangeInfo& r,
-                 const double* node_w, int32_t* inter, double* score, unsigned long long* counter, cudaStream_t s) {
+                 const double* node_w, int32_t* inter, double* score, double* jaccard, unsigned long long* counter,
+                 cudaStream_t s) {
     if (count <= 0) return GSP_OK;
-    const size_t smem = owner_smem_bytes(cls, kMode == 1);
+    const size_t smem = owner_smem_bytes(cls, kMode != 0);
     GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode, kScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
     cta_owner_kernel<kMode, kScatter><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, g->rev_off, r, node_w, inter,
-                                                                  score, counter);
+                                                                  score, jaccard, counter);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
 
 template <int kMode, bool kScatter>
 int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w, int32_t* inter,
-           double* score, cudaStream_t s, double* const* slices = nullptr, int64_t slice_len = 0) {
+           double* score, double* jaccard, cudaStream_t s, double* const* slices = nullptr, int64_t slice_len = 0,
+           double* const* slices2 = nullptr) {
     if (g->n == 0 || e_end == e_begin || owner_hi <= owner_lo) return GSP_OK;
     if (int rc = ensure_items(g, s)) return rc;
-    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi, slices, slice_len};
+    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi, slices, slice_len,
+                slices2};
     if (!r.full) {
         Scratch<int32_t> rr;
         GSP_CUDA_TRY(rr.alloc(2, s));
@@ -688,7 +709,7 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
         r.row_hi = h[1];
     }
     Scratch<double> squared;
-    if (kMode == 1) {
+    if (kMode != 0) {
         GSP_CUDA_TRY(squared.alloc(g->n, s));
         square_weights_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, node_w, squared.ptr);
         GSP_CHECK_LAUNCH();
@@ -702,12 +723,12 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     int hub_ctas = 2;
     const OwnerClass hub = hub_class_from_env(hub_ctas);
     if (int rc = launch_class<kMode, kScatter>(hub, items + g->num_owner_items, g->num_hub_items, hub_ctas, g, r, node_w, inter, score,
-                                     counters.ptr, s)) return rc;
-    if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score,
+                                     jaccard, counters.ptr, s)) return rc;
+    if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score, jaccard,
                                      counters.ptr + 1, s)) return rc;
     const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
     warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter,
-                                                                            score, counters.ptr + 2);
+                                                                            score, jaccard, counters.ptr + 2);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
@@ -736,18 +757,26 @@ __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr,
 
 int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
                             double* score, cudaStream_t s) {
-    return launch<0, false>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, s);
+    return launch<0, false>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, nullptr, s);
 }
 
 int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
                                 const double* node_w, double* score, cudaStream_t s) {
-    return launch<1, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, s);
+    return launch<1, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, nullptr, s);
 }
 
+// one streaming pass, both scores (and optionally the counts)
+int owner_intersect_both(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w,
+                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s) {
+    return launch<2, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, inter, adamic_adar, jaccard, s);
+}
+
+// mode 0: Jaccard into `slices`; 1: Adamic-Adar into `slices`; 2: Adamic-Adar into `slices`, Jaccard into `slices2`
 int owner_intersect_scatter(Graph* g, int mode, int64_t owner_lo, int64_t owner_hi, const double* node_w,
-                            double* const* slices, int64_t slice_len, cudaStream_t s) {
-    return mode == 0 ? launch<0, true>(g, 0, g->nnz, owner_lo, owner_hi, nullptr, nullptr, nullptr, s, slices, slice_len)
-                     : launch<1, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, s, slices, slice_len);
+                            double* const* slices, int64_t slice_len, cudaStream_t s, double* const* slices2) {
+    if (mode == 0) return launch<0, true>(g, 0, g->nnz, owner_lo, owner_hi, nullptr, nullptr, nullptr, nullptr, s, slices, slice_len);
+    if (mode == 1) return launch<1, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, slices, slice_len);
+    return launch<2, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, slices, slice_len, slices2);
 }
 
 int owner_costs(const Graph* g, double* cost, cudaStream_t s) {

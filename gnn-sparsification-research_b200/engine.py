@@ -134,6 +134,22 @@ class DeviceGraph:
             check(self._lib.gsp_adamic_adar(self._handle, ptr(node_weights), b, e, ptr(score), self._stream()))
         return score
 
+    def jaccard_adamic_adar(self, node_weights: Optional[torch.Tensor] = None, e_begin=None, e_end=None, return_counts=False,
+                            out_jaccard=None, out_adamic_adar=None):
+        """Both neighbourhood scores from ONE streaming pass (bit-identical to `jaccard()` and `adamic_adar()`)."""
+        b, e = self._range(e_begin, e_end)
+        if node_weights is not None:
+            node_weights = node_weights.to(device=self.device, dtype=torch.float64).contiguous()
+            if node_weights.numel() != self.num_nodes:
+                raise ValueError("node_weights must have num_nodes entries")
+        jac = self._empty(e - b, torch.float64) if out_jaccard is None else out_jaccard
+        aa = self._empty(e - b, torch.float64) if out_adamic_adar is None else out_adamic_adar
+        inter = self._empty(e - b, torch.int32) if return_counts else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_jaccard_adamic_adar(self._handle, ptr(node_weights), b, e, ptr(inter), ptr(jac), ptr(aa),
+                                                    self._stream()))
+        return (jac, aa, inter) if return_counts else (jac, aa)
+
     # -- owner-sharded scoring (multi-GPU; see sharding.py) -------------------------------------------
     def owner_costs(self) -> torch.Tensor:
         cost = self._empty(self.num_nodes, torch.float64)
@@ -153,10 +169,18 @@ class DeviceGraph:
                                                   self._stream()))
         return out
 
+    def jaccard_adamic_adar_owned(self, node_weights: Optional[torch.Tensor], node_begin: int, node_end: int,
+                                  out_jaccard: torch.Tensor, out_adamic_adar: torch.Tensor):
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_jaccard_adamic_adar_owned(self._handle, ptr(node_weights), int(node_begin), int(node_end),
+                                                          ptr(out_jaccard), ptr(out_adamic_adar), self._stream()))
+        return out_jaccard, out_adamic_adar
+
     def owned_scatter(self, metric: str, node_begin: int, node_end: int, slices_dev_ptr: int, world: int, slice_len: int,
-                      node_weights: Optional[torch.Tensor] = None) -> None:
+                      node_weights: Optional[torch.Tensor] = None, jaccard_slices_dev_ptr: Optional[int] = None) -> None:
         """Score the pairs owned by [node_begin, node_end) and store every score straight into the owning rank's slice;
-        `slices_dev_ptr` is the device address of an array of `world` slice base pointers (peer memory allowed)."""
+        `slices_dev_ptr` is the device address of an array of `world` slice base pointers (peer memory allowed).
+        metric "jaccard+adamic_adar": Adamic-Adar goes to `slices_dev_ptr`, Jaccard to `jaccard_slices_dev_ptr`."""
         sl = C.c_void_p(int(slices_dev_ptr))
         with torch.cuda.device(self.device):
             if metric == "jaccard":
@@ -165,6 +189,10 @@ class DeviceGraph:
             elif metric == "adamic_adar":
                 check(self._lib.gsp_adamic_adar_owned_scatter(self._handle, ptr(node_weights), int(node_begin), int(node_end), sl,
                                                               int(world), int(slice_len), self._stream()))
+            elif metric == "jaccard+adamic_adar":
+                check(self._lib.gsp_jaccard_adamic_adar_owned_scatter(
+                    self._handle, ptr(node_weights), int(node_begin), int(node_end), C.c_void_p(int(jaccard_slices_dev_ptr)), sl,
+                    int(world), int(slice_len), self._stream()))
             else:
                 raise ValueError(metric)
 

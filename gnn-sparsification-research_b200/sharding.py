@@ -90,6 +90,28 @@ def owner_sharded_scores(graph, metric: str, group, node_range: Tuple[int, int],
     return out
 
 
+def owner_sharded_jaccard_adamic_adar(graph, group, node_range: Tuple[int, int], node_weights=None,
+                                      scratch: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Both neighbourhood scores from one streaming pass per rank (`gsp_jaccard_adamic_adar_owned`), then one
+    reduce-scatter of the two zero-filled full-length vectors laid out as [world, 2, length] — returns this rank's
+    (jaccard, adamic_adar) slices."""
+    world = dist.get_world_size(group)
+    length, _ = equal_slices(graph.nnz, world)
+    need = 2 * length * world
+    both = scratch if scratch is not None and scratch.numel() >= need else torch.empty(need, dtype=torch.float64, device=graph.device)
+    both = both[:need]
+    both.zero_()
+    jac_full, aa_full = both[:length * world], both[length * world:]
+    graph.jaccard_adamic_adar_owned(node_weights, node_range[0], node_range[1], jac_full, aa_full)
+    if world == 1:
+        return jac_full[:length], aa_full[:length]
+    # rank k's output chunk = [jaccard slice k | adamic-adar slice k]
+    send = torch.stack((jac_full.view(world, length), aa_full.view(world, length)), dim=1).contiguous()
+    out = torch.empty(2 * length, dtype=torch.float64, device=graph.device)
+    dist.reduce_scatter_tensor(out, send.view(-1), group=group)
+    return out[:length], out[length:]
+
+
 class PeerScoreSlices:
     """Per-rank fp64 score slices in NVLink-mapped symmetric memory (torch.distributed._symmetric_memory).
 
@@ -119,6 +141,19 @@ def owner_sharded_scores_p2p(graph, metric: str, peer: PeerScoreSlices, node_ran
     graph.owned_scatter(metric, node_range[0], node_range[1], peer.slices_dev_ptr, peer.world, peer.length, node_weights)
     peer.barrier()                      # all peers' stores into this rank's slice have landed
     return peer.tensor
+
+
+def owner_sharded_jaccard_adamic_adar_p2p(graph, peer_jaccard: PeerScoreSlices, peer_adamic_adar: PeerScoreSlices,
+                                          node_range: Tuple[int, int], node_weights=None):
+    """Fused pass + fused exchange: one streaming kernel per rank stores both scores of every pair it owns straight into
+    the owning ranks' slices (two symmetric-memory buffers)."""
+    peer_jaccard.barrier()
+    peer_adamic_adar.barrier()
+    graph.owned_scatter("jaccard+adamic_adar", node_range[0], node_range[1], peer_adamic_adar.slices_dev_ptr, peer_adamic_adar.world,
+                        peer_adamic_adar.length, node_weights, jaccard_slices_dev_ptr=peer_jaccard.slices_dev_ptr)
+    peer_jaccard.barrier()
+    peer_adamic_adar.barrier()
+    return peer_jaccard.tensor, peer_adamic_adar.tensor
 
 
 def column_slice(k: int, rank: int, world: int) -> Tuple[int, int]:

@@ -102,6 +102,14 @@ int gsp_aa_node_weights(const gsp_graph* g, double* d_node_w, void* stream);
 int gsp_aa_node_weights_from_table(const gsp_graph* g, const double* d_table, int64_t table_len, double* d_node_w,
                                    void* stream);
 
+/* Jaccard and Adamic-Adar in ONE streaming pass (callers that score a graph with both metrics — the reference's
+ * ablation loop, src/experiments/ablation.py:220-270, and scripts/nb05_roman_empire/roman_empire_gpu.py:81-102 do):
+ * the hit ballots the ordered Adamic-Adar sum needs also give the intersection count, so d_jaccard / d_inter come
+ * at the price of the Adamic-Adar pass alone. Bit-identical to gsp_jaccard + gsp_adamic_adar (asymmetric graphs run
+ * the two passes internally: their intersections differ). d_inter may be NULL. */
+int gsp_jaccard_adamic_adar(const gsp_graph* g, const double* d_node_w, int64_t e_begin, int64_t e_end, int32_t* d_inter,
+                            double* d_jaccard, double* d_adamic_adar, void* stream);
+
 /* Owner-sharded variants for multi-GPU scoring of a SYMMETRIC graph: every undirected pair {u,v} is evaluated on
  * exactly one rank — the one whose node range [node_begin, node_end) holds the pair's owner (the endpoint with the
  * larger degree, ties: smaller id) — and its score is written at BOTH directed positions of full-length (nnz)
@@ -112,6 +120,8 @@ int gsp_jaccard_owned(const gsp_graph* g, int64_t node_begin, int64_t node_end, 
                       double* d_score_full, void* stream);
 int gsp_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
                           double* d_score_full, void* stream);
+int gsp_jaccard_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                  double* d_jaccard_full, double* d_adamic_adar_full, void* stream);
 int gsp_owner_costs(const gsp_graph* g, double* d_cost, void* stream);
 /* Fused scoring + exchange: like the *_owned calls, but every score is stored by the scoring kernel directly into the
  * slice of the rank that owns its position — d_slices is a DEVICE array of `world` pointers, d_slices[k] = base of rank
@@ -122,6 +132,9 @@ int gsp_jaccard_owned_scatter(const gsp_graph* g, int64_t node_begin, int64_t no
                               int32_t world, int64_t slice_len, void* stream);
 int gsp_adamic_adar_owned_scatter(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
                                   double* const* d_slices, int32_t world, int64_t slice_len, void* stream);
+int gsp_jaccard_adamic_adar_owned_scatter(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
+                                          double* const* d_jaccard_slices, double* const* d_adamic_adar_slices,
+                                          int32_t world, int64_t slice_len, void* stream);
 
 /* degree product — replaces reference core.py:167-172 (`degree` metric; raw-value row sums). */
 int gsp_degree_product(const gsp_graph* g, int64_t e_begin, int64_t e_end, double* d_score, void* stream);

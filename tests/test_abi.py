@@ -126,4 +126,4 @@ def test_profiles_traffic_record_is_well_formed():
     t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
     assert t["workload"] == {"scale": 24, "edge_factor": 16, "dim": 128, "n_gpus": 1}
     for k in ("jaccard", "adamic_adar"):
-        assert t[k]["dram_bytes_per_launch"] > 1e11
+        assert 1e10 < t[k]["dram_bytes_per_launch"] < 1e12

@@ -692,3 +692,89 @@ def test_peer_scatter_scoring_with_emulated_ranks():
         got = torch.cat(bufs)[: g.nnz]
         assert torch.equal(got, full), metric
         assert bool((torch.cat(bufs)[g.nnz:] == -1.0).all())          # padding positions are never written
+
+
+# ----------------------------------------------------------------------------- fused Jaccard + Adamic-Adar pass
+@pytest.mark.parametrize("case", ["hub", "roman_empire", "cora", "rmat", "karate_unsorted", "asymmetric"])
+def test_fused_jaccard_adamic_adar_pass_against_oracle(case):
+    """gsp_jaccard_adamic_adar: one streaming pass, both score vectors and the counts bit-equal to the oracle (and so to
+    the two separate passes); asymmetric patterns take the two-pass route inside the call."""
+    if case == "hub":
+        ei, n = hub_graph()
+    elif case in ("roman_empire", "cora"):
+        ei, _, n = named_graph(case)
+    elif case == "rmat":
+        n = 1 << 15
+        ei = rmat_graph(n, 16 * n, 15, seed=21)
+    elif case == "karate_unsorted":
+        ei, n = _karate_unsorted()
+    else:
+        rng = np.random.default_rng(4)
+        n = 500
+        keys = np.unique(rng.integers(0, n, 6000) * n + rng.integers(0, n, 6000))
+        ei = np.vstack([keys // n, keys % n])
+    sp = make_sparsifier(ei, n)
+    g = sp.graph
+    assert g.symmetric == (case != "asymmetric")
+    csr = co.csr_from_edge_index(ei, n)
+    want_j, want_inter = co.calculate_jaccard_scores(csr, return_counts=True)
+    want_a = co.calculate_adamic_adar_scores(csr)
+    w = g.aa_node_weights_numpy()
+    jac, aa, inter = g.jaccard_adamic_adar(w, return_counts=True)
+    assert np.array_equal(inter.cpu().numpy(), want_inter)
+    assert bits_equal(jac.cpu().numpy(), want_j)
+    assert bits_equal(aa.cpu().numpy(), want_a)
+    # edge-range slices of the fused pass reassemble to the full vectors
+    e = g.nnz
+    cuts = [0, 1, e // 3, e // 3 + 1, e - 2, e] if e > 8 else [0, e]
+    parts = [g.jaccard_adamic_adar(w, cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), jac) and torch.equal(torch.cat([p[1] for p in parts]), aa)
+
+
+def test_prefetch_scores_fuses_without_changing_results():
+    ei, x, n = named_graph("roman_empire")
+    a = make_sparsifier(ei, n, x)
+    b = make_sparsifier(ei, n, x)
+    launches = gsr_b200._lib.load().gsp_launch_count
+    b.prefetch_scores(["jaccard", "adamic_adar", "feature_cosine"])
+    before = launches()
+    got = {m: b.compute_scores(m) for m in ("jaccard", "adamic_adar", "feature_cosine")}
+    assert launches() == before                                   # everything was already on the device
+    for m, s in got.items():
+        assert bits_equal(s, a.compute_scores(m)), m
+    for m in ("jaccard", "aa"):
+        _, ma = a.sparsify(m, 0.6, return_mask=True)
+        _, mb = b.sparsify(m, 0.6, return_mask=True)
+        assert torch.equal(ma, mb)
+    with pytest.raises(ValueError):
+        b.prefetch_scores(["jaccard", "no_such_metric"])
+
+
+def test_fused_pass_owner_shards_and_peer_scatter():
+    """Multi-GPU forms of the fused pass on one device: owned (zero-filled full vectors summed over three node ranges) and
+    scatter (every score stored into the slice that owns its position), both equal to the single-GPU vectors."""
+    from gsr_b200 import sharding
+
+    ei, n = hub_graph(n=12000, hub_deg=9000, extra=30000, seed=8)
+    g = make_sparsifier(ei, n).graph
+    w = g.aa_node_weights()
+    full_j, full_a = g.jaccard(), g.adamic_adar(w)
+    cuts = sharding.balanced_cuts(torch.cumsum(g.owner_costs(), 0), 3)
+    length, _ = sharding.equal_slices(g.nnz, 3)
+    acc_j = torch.zeros(g.nnz, dtype=torch.float64, device=DEV)
+    acc_a = torch.zeros_like(acc_j)
+    bufs_j = [torch.full((length,), -1.0, dtype=torch.float64, device=DEV) for _ in range(3)]
+    bufs_a = [torch.full((length,), -1.0, dtype=torch.float64, device=DEV) for _ in range(3)]
+    ptr_j = torch.tensor([b.data_ptr() for b in bufs_j], dtype=torch.int64, device=DEV)
+    ptr_a = torch.tensor([b.data_ptr() for b in bufs_a], dtype=torch.int64, device=DEV)
+    for r in range(3):
+        bj = torch.zeros(g.nnz, dtype=torch.float64, device=DEV)
+        ba = torch.zeros_like(bj)
+        g.jaccard_adamic_adar_owned(w, cuts[r], cuts[r + 1], bj, ba)
+        acc_j += bj
+        acc_a += ba
+        g.owned_scatter("jaccard+adamic_adar", cuts[r], cuts[r + 1], ptr_a.data_ptr(), 3, length, w,
+                        jaccard_slices_dev_ptr=ptr_j.data_ptr())
+    assert torch.equal(acc_j, full_j) and torch.equal(acc_a, full_a)
+    assert torch.equal(torch.cat(bufs_j)[: g.nnz], full_j) and torch.equal(torch.cat(bufs_a)[: g.nnz], full_a)
+    assert bool((torch.cat(bufs_j)[g.nnz:] == -1.0).all()) and bool((torch.cat(bufs_a)[g.nnz:] == -1.0).all())
