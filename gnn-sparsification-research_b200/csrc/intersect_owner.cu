@@ -307,33 +307,10 @@ __host__ __device__ inline size_t owner_smem_bytes(const OwnerClass& c, bool ord
            (ordered_sum ? (size_t)(c.threads / kWarp) * kQueueStride * sizeof(double) : 0);
 }
 
-// Process the part of row(w) below `cursor` that lies in the current tile's id range [lo_id, +inf), walking DOWN
-// (ids descending: SciPy's Adamic-Adar accumulation order; Jaccard does not care). Four 32-id groups are loaded
-// per round so a long row keeps four requests in flight. Out-of-row lanes carry an INT_MIN sentinel that fails
-// every test, so the loop body is branch-free. kBounded = false is the owner's lowest tile (no id bound: the rest
-// of the row is consumed) — the only pass single-tile owners ever run. Returns the new cursor.
-// Ordered accumulation of one 32-id group: the hit lanes park their terms in a warp-private shared queue in
-// descending-id order, then every lane replays the queue (broadcast loads) with the sequential fp64 adds the
-// reference's SpGEMM performs. ~3 issue slots per hit instead of ~8 for a ballot/shuffle loop.
-template <int kMode>
-__device__ __forceinline__ void accumulate_hits(bool hit, double w, double* queue, double& acc, int& nhits) {
-    const unsigned hits = __ballot_sync(0xffffffffu, hit);
-    if (hits == 0) return;
-    const int n = __popc(hits);
-    nhits += n;   // warp-uniform; dead code unless the fused pass reads it
-    if (hit) queue[__popc(hits & ((1u << lane_id()) - 1u))] = w;   // lanes ascending == ids descending; w = weight squared
-    if (lane_id() < 3) queue[n + lane_id()] = 0.0;   // pad to a multiple of four: acc + 0.0 == acc (acc >= 0)
-    __syncwarp();
-    for (int h = 0; h < n; h += 4) {                 // two 16-byte broadcast loads + four ordered adds per step
-        const double2 a = *reinterpret_cast<const double2*>(queue + h);
-        const double2 b = *reinterpret_cast<const double2*>(queue + h + 2);
-        acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, a.x), a.y), b.x), b.y);
-    }
-    __syncwarp();
-}
-
-// Two consecutive 32-id groups (group 0 holds the larger ids) through one queue pass: one padding store, one pair of
-// warp barriers and one replay loop for up to 64 hits.
+// Ordered accumulation of two consecutive 32-id groups (group 0 holds the larger ids): the hit lanes park their terms in
+// a warp-private shared queue in descending-id order, then every lane replays the queue (broadcast loads) with the
+// sequential fp64 adds the reference's SpGEMM performs — ~3 issue slots per hit instead of ~8 for a ballot/shuffle
+// loop; one padding store, one pair of warp barriers and one replay loop serve up to 64 hits.
 __device__ __forceinline__ void accumulate_hits2(bool hit0, double w0, bool hit1, double w1, double* queue, double& acc,
                                                  int& nhits) {
     const unsigned h0 = __ballot_sync(0xffffffffu, hit0);
@@ -355,6 +332,11 @@ __device__ __forceinline__ void accumulate_hits2(bool hit0, double w0, bool hit1
     __syncwarp();
 }
 
+// Process the part of row(w) below `cursor` that lies in the current tile's id range [lo_id, +inf), walking DOWN
+// (ids descending: SciPy's Adamic-Adar accumulation order; Jaccard does not care). Several 32-id groups are loaded
+// per round so a long row keeps several requests in flight. Out-of-row lanes carry an INT_MIN sentinel that fails
+// every test. kBounded = false is the owner's lowest tile (no id bound: the rest of the row is consumed) — the only
+// pass single-tile owners ever run. Returns the new cursor.
 template <int kMode, bool kBounded>
 __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, int cursor, int32_t lo_id,
                                            const Cuckoo& table, const double* __restrict__ node_w, double* queue,
@@ -411,6 +393,28 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
             }
         }
         cursor = 0;
+    } else if (kMode != 0) {
+        // Branch-free rounds of two groups: ids below the tile are not in its table, so both groups are probed and
+        // accumulated wherever the boundary falls; the in-tile ids are a prefix of the 64 visited (ids descend).
+        const bool no_stash = table.stash_n == 0;
+        for (;;) {
+            const int top = cursor - 1 - lane;
+            const int32_t x0 = top >= 0 ? __ldg(row_w + top) : INT_MIN;
+            const int32_t x1 = top - kWarp >= 0 ? __ldg(row_w + top - kWarp) : INT_MIN;
+            bool h0, h1;
+            if (no_stash) {
+                h0 = cuckoo_hit(table, x0);
+                h1 = cuckoo_hit(table, x1);
+            } else {
+                h0 = cuckoo_contains(table, x0);
+                h1 = cuckoo_contains(table, x1);
+            }
+            const double w0 = h0 ? __ldg(node_w + x0) : 0.0, w1 = h1 ? __ldg(node_w + x1) : 0.0;
+            const int used = __popc(__ballot_sync(0xffffffffu, x0 >= lo_id)) + __popc(__ballot_sync(0xffffffffu, x1 >= lo_id));
+            accumulate_hits2(h0, w0, h1, w1, queue, acc, nh);
+            cursor -= used;
+            if (used < 2 * kWarp || cursor <= 0) break;   // ran off the tile or the row
+        }
     } else {
         bool done = false;
         int groups = 1;   // a tile usually holds a short piece of the row: probe one group before going four deep
@@ -424,7 +428,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
                 if (done || k >= groups) break;
                 const bool in_tile = x[k] >= lo_id;   // sentinel lanes fail (lo_id > INT_MIN)
                 const bool hit = in_tile && cuckoo_contains(table, x[k]);
-                if (kMode == 0) c += hit; else accumulate_hits<kMode>(hit, hit ? __ldg(node_w + x[k]) : 0.0, queue, acc, nh);
+                c += hit;
                 const unsigned inside = __ballot_sync(0xffffffffu, in_tile);
                 if (inside != 0xffffffffu) {           // ran off the tile (or the row): stop after this group
                     done = true;
@@ -442,7 +446,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
 }
 
 template <int kMode, bool kScatter>
-__global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t num_items, OwnerClass cls,
+__device__ __forceinline__ void cta_owner_body(const OwnerItem* __restrict__ items, int64_t num_items, OwnerClass cls,
                                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                  const int32_t* __restrict__ rev_off, RangeInfo r,
                                  const double* __restrict__ node_w, int32_t* __restrict__ inter_out,
@@ -560,6 +564,23 @@ __global__ void cta_owner_kernel(const OwnerItem* __restrict__ items, int64_t nu
                                         jaccard_out);
         }
     }
+}
+
+#define GSP_OWNER_PARAMS                                                                                              \
+    const OwnerItem *__restrict__ items, int64_t num_items, OwnerClass cls, const int64_t *__restrict__ indptr,             \
+        const int32_t *__restrict__ indices, const int32_t *__restrict__ rev_off, RangeInfo r,                              \
+        const double *__restrict__ node_w, int32_t *__restrict__ inter_out, double *__restrict__ score_out,                 \
+        double *__restrict__ jaccard_out, unsigned long long *counter
+#define GSP_OWNER_ARGS items, num_items, cls, indptr, indices, rev_off, r, node_w, inter_out, score_out, jaccard_out, counter
+
+// No launch bounds: the natural allocation is 32-40 registers (two 768-thread hub CTAs per SM); bounding every
+// instantiation measured 5 % slower. Only the fused pass with peer scatter needs the cap (47 registers otherwise).
+template <int kMode, bool kScatter>
+__global__ void cta_owner_kernel(GSP_OWNER_PARAMS) {
+    cta_owner_body<kMode, kScatter>(GSP_OWNER_ARGS);
+}
+__global__ void __launch_bounds__(768, 2) cta_owner_kernel_both_scatter(GSP_OWNER_PARAMS) {
+    cta_owner_body<2, true>(GSP_OWNER_ARGS);
 }
 
 // ---- work items for level B (built once per graph) -----------------------------------------------------------
@@ -680,11 +701,13 @@ int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, i
                  cudaStream_t s) {
     if (count <= 0) return GSP_OK;
     const size_t smem = owner_smem_bytes(cls, kMode != 0);
-    GSP_CUDA_TRY(cudaFuncSetAttribute(cta_owner_kernel<kMode, kScatter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    auto kernel = cta_owner_kernel<kMode, kScatter>;
+    if constexpr (kMode == 2 && kScatter) kernel = cta_owner_kernel_both_scatter;
+    GSP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
-    cta_owner_kernel<kMode, kScatter><<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, g->rev_off, r, node_w, inter,
-                                                                  score, jaccard, counter);
+    kernel<<<(int)blocks, cls.threads, smem, s>>>(items, count, cls, g->indptr, g->indices, g->rev_off, r, node_w, inter, score, jaccard,
+                                                  counter);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
