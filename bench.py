@@ -267,6 +267,7 @@ def main() -> None:
     group = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines stay off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     lib = _lib.load()

@@ -77,7 +77,8 @@ def owner_sharded_scores(graph, metric: str, group, node_range: Tuple[int, int],
     rank its contiguous slice of `equal_slices(nnz, world)`. NCCL over NVLink; fp64 [nnz] crosses the fabric once."""
     world = dist.get_world_size(group)
     length, _ = equal_slices(graph.nnz, world)
-    full = scratch if scratch is not None else torch.empty(length * world, dtype=torch.float64, device=graph.device)
+    full = (scratch[: length * world] if scratch is not None and scratch.numel() >= length * world
+            else torch.empty(length * world, dtype=torch.float64, device=graph.device))
     full.zero_()
     if metric == "jaccard":
         graph.jaccard_owned(node_range[0], node_range[1], full)

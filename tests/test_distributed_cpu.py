@@ -126,3 +126,73 @@ def test_partition_helpers():
     assert slices[0] == (0, 8) and slices[-1] == (56, 64)
     slices = [sharding.column_slice(10, r, 4) for r in range(4)]
     assert sum(hi - lo for lo, hi in slices) == 10 and all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
+
+
+class _OwnedScoresStandIn:
+    """Stand-in for engine.DeviceGraph in the owner-sharded exchange: position p is "owned" by node p % num_nodes, its
+    Jaccard score is p + 1 and its Adamic-Adar score 1000 + p (the CUDA calls write exactly the owned positions of
+    zero-filled full-length buffers; here NumPy-style indexing does)."""
+
+    def __init__(self, nnz, num_nodes):
+        self.nnz, self.num_nodes, self.device = nnz, num_nodes, torch.device("cpu")
+        self.pos = torch.arange(nnz)
+
+    def _owned(self, node_begin, node_end):
+        owner = self.pos % self.num_nodes
+        return (owner >= node_begin) & (owner < node_end)
+
+    def jaccard_owned(self, node_begin, node_end, out, counts=None):
+        m = self._owned(node_begin, node_end)
+        out[: self.nnz][m] = (self.pos[m] + 1).double()
+        return out
+
+    def adamic_adar_owned(self, node_weights, node_begin, node_end, out):
+        m = self._owned(node_begin, node_end)
+        out[: self.nnz][m] = (self.pos[m] + 1000).double()
+        return out
+
+    def jaccard_adamic_adar_owned(self, node_weights, node_begin, node_end, out_jaccard, out_adamic_adar):
+        self.jaccard_owned(node_begin, node_end, out_jaccard)
+        self.adamic_adar_owned(node_weights, node_begin, node_end, out_adamic_adar)
+        return out_jaccard, out_adamic_adar
+
+
+def _owner_exchange_worker(rank, world, port, nnz, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = _OwnedScoresStandIn(nnz, 10)
+        node_range = (0, 4) if rank == 0 else (4, 10)
+        length, slices = sharding.equal_slices(nnz, world)
+        lo, hi = slices[rank]
+        res = {}
+        for scratch in (None, torch.empty(2 * length * world, dtype=torch.float64)):    # the bench shares one 2x scratch
+            tag = "none" if scratch is None else "shared"
+            res[f"j_{tag}"] = sharding.owner_sharded_scores(g, "jaccard", None, node_range, scratch=scratch)[: hi - lo].clone()
+            res[f"a_{tag}"] = sharding.owner_sharded_scores(g, "adamic_adar", None, node_range, scratch=scratch)[: hi - lo].clone()
+            j, a = sharding.owner_sharded_jaccard_adamic_adar(g, None, node_range, scratch=scratch)
+            res[f"fj_{tag}"], res[f"fa_{tag}"] = j[: hi - lo].clone(), a[: hi - lo].clone()
+        out.put((rank, lo, hi, {k: v.numpy() for k, v in res.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_owner_sharded_exchange_world2():
+    """Reduce-scatter form of the owner-sharded Jaccard / Adamic-Adar exchange (separate and fused passes), with and without
+    a caller-provided scratch buffer that is larger than one full vector."""
+    nnz = 1001                                   # not divisible by the world size: the last slice is padded
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_owner_exchange_worker, args=(r, 2, port, nnz, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pos = np.arange(nnz, dtype=np.float64)
+    for rank, lo, hi, res in got:
+        for tag in ("none", "shared"):
+            assert np.array_equal(res[f"j_{tag}"], pos[lo:hi] + 1) and np.array_equal(res[f"fj_{tag}"], pos[lo:hi] + 1), (rank, tag)
+            assert np.array_equal(res[f"a_{tag}"], pos[lo:hi] + 1000) and np.array_equal(res[f"fa_{tag}"], pos[lo:hi] + 1000), (rank, tag)
