@@ -42,6 +42,7 @@ PROTOTYPES = {
     "gsp_version": (_INT, []),
     "gsp_last_error": (C.c_char_p, []),
     "gsp_launch_count": (C.c_uint64, []),
+    "gsp_trim_scratch": (_INT, []),
     "gsp_graph_create": (_INT, [_I64, _I64, _P, _P, _P, _P, C.POINTER(_P)]),
     "gsp_graph_destroy": (None, [_P]),
     "gsp_graph_get_info": (_INT, [_P, C.POINTER(GraphInfo)]),
@@ -60,6 +61,9 @@ PROTOTYPES = {
     "gsp_jaccard_owned_scatter": (_INT, [_P, _I64, _I64, _P, _I32, _I64, _P]),
     "gsp_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _I32, _I64, _P]),
     "gsp_jaccard_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _P, _I32, _I64, _P]),
+    "gsp_gcn_norm": (_INT, [_I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gsp_target_order": (_INT, [_I64, _I64, _P, _P, _P, _P]),
+    "gsp_gcn_propagate": (_INT, [_I64, _P, _P, _P, _P, _P, _I32, _I64, _P, _I64, _P]),
     "gsp_degree_product": (_INT, [_P, _I64, _I64, _P, _P]),
     "gsp_featcos_normalize_f32": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
     "gsp_featcos_f32": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),

@@ -45,6 +45,11 @@ void count_launch();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// graph.cu: once per device, lets the default stream-ordered pool KEEP freed scratch across synchronisation points (the
+// default release threshold of 0 hands everything back to the driver at every sync, and the next call pays the mapping
+// of its scratch again: ~50 ms per call for the 134 MB weight table of the Adamic-Adar pass). gsp_trim_scratch releases it.
+void configure_scratch_pool();
+
 // Stream-ordered scratch buffer (cudaMallocAsync pool): freed on the same stream when it goes out of scope.
 template <typename T>
 struct Scratch {
@@ -52,6 +57,7 @@ struct Scratch {
     cudaStream_t stream = nullptr;
     cudaError_t alloc(size_t count, cudaStream_t s) {
         stream = s;
+        configure_scratch_pool();
         return cudaMallocAsync(reinterpret_cast<void**>(&ptr), (count ? count : 1) * sizeof(T), s);
     }
     ~Scratch() {

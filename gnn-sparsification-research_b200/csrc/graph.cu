@@ -393,6 +393,19 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
 
 int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s) { return inclusive_sum(in, out, count, s); }
 
+void configure_scratch_pool() {
+    static std::atomic<uint64_t> configured{0};   // one bit per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if ((configured.load(std::memory_order_relaxed) >> dev) & 1ull) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
 int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
                        cudaStream_t s) {
     size_t tmp_bytes = 0;
@@ -412,6 +425,16 @@ GSP_API int gsp_version(void) { return GSP_VERSION; }
 GSP_API const char* gsp_last_error(void) { return gsp::g_error; }
 
 GSP_API uint64_t gsp_launch_count(void) { return gsp::g_launches.load(std::memory_order_relaxed); }
+
+GSP_API int gsp_trim_scratch(void) {
+    int dev = 0;
+    GSP_CUDA_TRY(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    GSP_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    GSP_CUDA_TRY(cudaDeviceSynchronize());
+    GSP_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return GSP_OK;
+}
 
 GSP_API int gsp_graph_create(int64_t num_nodes, int64_t num_edges, const int64_t* d_row, const int64_t* d_col,
                              const double* d_val, void* stream, gsp_graph** out) {

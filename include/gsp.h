@@ -62,6 +62,9 @@ int gsp_version(void);
 const char* gsp_last_error(void);
 /* Number of CUDA kernels this library has launched in the process so far (monotonic; for benchmarks). */
 uint64_t gsp_launch_count(void);
+/* The library keeps its stream-ordered scratch (cudaMallocAsync default pool of the current device) across calls;
+ * this hands the unused part back to the driver (synchronises the device). */
+int gsp_trim_scratch(void);
 
 /* ---- graph ----------------------------------------------------------------------------------
  * Replaces reference core.py:70-74: sp.csr_matrix((ones(E), (row, col)), shape=(n, n)).
@@ -234,6 +237,28 @@ int gsp_degree_aware_guarantee(const int64_t* d_src, const double* d_scores, int
 int gsp_compact_edges(const int64_t* d_edge_index, int64_t ld, int64_t count, const uint8_t* d_mask,
                       const double* d_scores, int invert_weights, int64_t* d_out_edge_index, int64_t out_ld,
                       float* d_out_weight, int64_t* d_num_kept, void* stream);
+
+/* ---- consumer side: GCN normalisation and propagation of the kept sub-graph ---------
+ * The reference trains GCN / GCN* on the sparsified graph with GCNConv(cached=False, normalize=True) and the
+ * optional "-W" edge weights (src/models/gnn.py:222-223,244), i.e. every layer of every forward pass re-runs
+ * torch_geometric's gcn_norm (torch-geometric >= 2.3, pyproject.toml:31; not vendored) and a scatter-add
+ * propagate on the same kept edges. gsp_gcn_norm restates gcn_norm(add_self_loops=True, improved=False,
+ * flow="source_to_target"): self-loop edges are dropped from the list, one loop per node is appended (weight =
+ * the node's LAST existing loop weight, else 1), deg[t] = sum of weights over edges INTO t (fp32, in list
+ * order), out_weight = deg^-1/2[row] * w * deg^-1/2[col] (inf -> 0). d_weight may be NULL (all ones). Output
+ * buffers hold num_edges + num_nodes entries; d_out_count (int64[1], device, optional) receives the count. */
+int gsp_gcn_norm(int64_t num_nodes, int64_t num_edges, const int64_t* d_row, const int64_t* d_col, const float* d_weight,
+                 int64_t* d_out_row, int64_t* d_out_col, float* d_out_weight, int64_t* d_out_count, void* stream);
+/* Stable grouping of an edge list by target: d_indptr int64[num_nodes + 1], d_perm int64[num_edges] (edge positions,
+ * targets ascending, list order kept inside a target). */
+int gsp_target_order(int64_t num_nodes, int64_t num_edges, const int64_t* d_col, int64_t* d_indptr, int64_t* d_perm,
+                     void* stream);
+/* GCNConv's propagate (sum aggregation at the targets): d_out[t, :] = sum over the edges e into t, in list order, of
+ * d_weight[e] * d_x[d_row[e], :] — fp32, multiply then add (no FMA), so the result equals a sequential CPU
+ * scatter-add bit for bit and does not change from run to run. d_x: fp32 [num_nodes, dim] with row stride ldx. */
+int gsp_gcn_propagate(int64_t num_nodes, const int64_t* d_indptr, const int64_t* d_perm, const int64_t* d_row,
+                      const float* d_weight, const float* d_x, int32_t dim, int64_t ldx, float* d_out, int64_t ldo,
+                      void* stream);
 
 #ifdef __cplusplus
 }

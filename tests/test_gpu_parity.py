@@ -778,3 +778,65 @@ def test_fused_pass_owner_shards_and_peer_scatter():
     assert torch.equal(acc_j, full_j) and torch.equal(acc_a, full_a)
     assert torch.equal(torch.cat(bufs_j)[: g.nnz], full_j) and torch.equal(torch.cat(bufs_a)[: g.nnz], full_a)
     assert bool((torch.cat(bufs_j)[g.nnz:] == -1.0).all()) and bool((torch.cat(bufs_a)[g.nnz:] == -1.0).all())
+
+
+# ----------------------------------------------------------------------------- GCN consumer
+def _gcn_case(case):
+    rng = np.random.default_rng(11)
+    if case == "roman_kept_weighted":
+        ei, _, n = named_graph("roman_empire")
+        sp = make_sparsifier(ei, n)
+        from gsr_b200.labels import sparsify_by_label
+        kept, w, _ = sparsify_by_label(sp, "Jaccard-T-W", 0.6)
+        return kept.edge_index.cpu().numpy(), w.cpu().numpy(), n
+    if case == "cora_unweighted":
+        ei, _, n = named_graph("cora")
+        return ei, None, n
+    if case == "loops_duplicates_isolated":
+        n = 40
+        row = rng.integers(0, 30, 400)
+        col = rng.integers(0, 30, 400)
+        row[:25] = col[:25]                                   # self loops, some nodes several times
+        return np.vstack([row, col]), rng.random(400).astype(np.float32) + 0.1, n   # nodes 30..39 isolated
+    if case == "hub_weighted":
+        ei, n = hub_graph(n=12000, hub_deg=9000, extra=30000, seed=8)
+        return ei, (rng.random(ei.shape[1]) + 0.05).astype(np.float32), n
+    raise ValueError(case)
+
+
+@pytest.mark.parametrize("case", ["roman_kept_weighted", "cora_unweighted", "loops_duplicates_isolated", "hub_weighted"])
+@pytest.mark.parametrize("dim", [128, 20, 130, 256])
+def test_gcn_norm_and_propagate_against_pyg_restatement(case, dim):
+    """gsp_gcn_norm / gsp_target_order / gsp_gcn_propagate against oracle/pyg_port.py: same edge list layout, weights and
+    propagated features BIT-equal (fp32, sums in edge order on both sides)."""
+    from gsr_b200.gcn import GcnPropagation, gcn_norm
+    from oracle import pyg_port
+
+    ei, w, n = _gcn_case(case)
+    want_ei, want_w = pyg_port.gcn_norm(ei, w, n)
+    got_ei, got_w = gcn_norm(torch.from_numpy(ei), None if w is None else torch.from_numpy(w), n, device=DEV)
+    assert np.array_equal(got_ei.cpu().numpy(), want_ei)
+    assert np.array_equal(got_w.cpu().numpy().view(np.uint32), want_w.view(np.uint32))
+    x = np.random.default_rng(3).standard_normal((n, dim)).astype(np.float32)
+    prop = GcnPropagation(torch.from_numpy(ei), None if w is None else torch.from_numpy(w), n, device=DEV)
+    got = prop(torch.from_numpy(x)).cpu().numpy()
+    want = pyg_port.propagate(want_ei, want_w, x, n)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # un-normalised operator (GCNConv(normalize=False) fed with precomputed weights) and a strided input
+    raw = GcnPropagation(got_ei, got_w, n, normalize=False, device=DEV)
+    wide = torch.zeros((n, dim + 4), dtype=torch.float32, device=DEV)
+    wide[:, :dim] = torch.from_numpy(x).to(DEV)
+    assert torch.equal(raw(wide[:, :dim]), prop(torch.from_numpy(x)))
+
+
+def test_gcn_norm_edge_cases():
+    from gsr_b200.gcn import GcnPropagation, gcn_norm
+
+    ei, w = gcn_norm(torch.zeros((2, 0), dtype=torch.int64), None, 3, device=DEV)      # no edges: identity
+    assert ei.cpu().tolist() == [[0, 1, 2], [0, 1, 2]] and w.cpu().tolist() == [1.0, 1.0, 1.0]
+    out = GcnPropagation(torch.zeros((2, 0), dtype=torch.int64), None, 3, device=DEV)(torch.eye(3))
+    assert torch.equal(out.cpu(), torch.eye(3))
+    with pytest.raises(ValueError):
+        gcn_norm(torch.tensor([[0, 5], [1, 0]]), None, 3, device=DEV)
+    with pytest.raises(ValueError):
+        gcn_norm(torch.tensor([[0, 1], [1, 0]]), torch.ones(3), 2, device=DEV)
