@@ -457,6 +457,7 @@ def main() -> None:
         d2h = 0
         times = []
         h2d_ms = []
+        breakdown = []
         for it in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
@@ -468,13 +469,23 @@ def main() -> None:
                 sp = gsr_b200.GraphSparsifier(data, str(dev))
                 if fused:
                     sp.prefetch_scores(METHODS)
+                marks = [("upload+graph+scoring", time.perf_counter())]      # (the scoring calls end with a device read-back)
                 d2h = 0
                 for m in METHODS:
                     s = sp.compute_scores(m)                                  # np.ndarray fp64 on host
+                    marks.append((m + ":scores_to_host", time.perf_counter()))
                     out, msk = sp.sparsify(m, RETENTION, return_mask=True)    # Data (edge_index on device) + host bool mask
+                    marks.append((m + ":sparsify", time.perf_counter()))
                     d2h += s.nbytes + msk.numel()
                     del out, msk
-                del sp, data
+                del sp, data, s
+                if it > 0:
+                    prev = t0
+                    row = {}
+                    for name, t in marks:
+                        row[name] = round((t - prev) * 1e3, 1)
+                        prev = t
+                    breakdown.append(row)
             else:
                 ei_d = ei_host.to(dev, non_blocking=True)
                 x_d = x_host.to(dev, non_blocking=True)
@@ -514,7 +525,7 @@ def main() -> None:
         e2e = {"value": len(METHODS) * e / float(t_e2e), "unit": "edges/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(t_e2e) * 1e3,
                "steps_ms": [round(t * 1e3, 1) for t in times], "h2d_ms": [round(t, 1) for t in h2d_ms],
-               "h2d_gbs": h2d / (sum(h2d_ms) / len(h2d_ms) * 1e-3) / 1e9, "api": api,
+               "h2d_gbs": h2d / (sum(h2d_ms) / len(h2d_ms) * 1e-3) / 1e9, "steps_breakdown_ms": breakdown, "api": api,
                "note": "bytes are per rank" if world > 1 else "single rank"}
 
     # ---- ApproxER sparsify ms (BASELINE config 4: products-shaped graph, JLT k = 64, CG rtol 1e-6, <= 500 iterations) ----

@@ -89,7 +89,19 @@ class GraphSparsifier:
             if ei.dtype != torch.int64:
                 ei = ei.long()
             self._ei_dev = ei.to(dev, non_blocking=True).contiguous()
-            self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
+            ready = getattr(self.data, "_gsp_edge_index_ready", None)
+            if ready is not None and ei.is_cuda and self._ei_dev.data_ptr() == ei.data_ptr():
+                # `Data.to(cuda, non_blocking=True)` marked the arrival of the edge list: build the CSR on a side stream that
+                # waits only for it, so the build overlaps the upload of the feature matrix queued behind it
+                main = torch.cuda.current_stream(dev)
+                side = torch.cuda.Stream(dev)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
+                self._ei_dev.record_stream(side)
+                main.wait_stream(side)
+            else:
+                self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
         return self._graph
 
     @property

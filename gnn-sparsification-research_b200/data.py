@@ -62,13 +62,29 @@ class Data:
     def clone(self) -> "Data":
         out = self.__class__.__new__(self.__class__)
         for key, value in self._items():
+            if key.startswith("_gsp_"):          # stream bookkeeping of `to()`, not data
+                continue
             out.__dict__[key] = value.clone() if torch.is_tensor(value) else copy.deepcopy(value)
         return out
 
     def to(self, device, non_blocking: bool = False) -> "Data":
+        """Move every tensor attribute. `edge_index` goes first and, for an asynchronous upload to a CUDA device, an event
+        marks its arrival: `GraphSparsifier` builds the CSR as soon as the edge list is there, while the (much larger)
+        feature matrix is still crossing PCIe."""
         out = self.__class__.__new__(self.__class__)
-        for key, value in self._items():
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        ordered = sorted(self._items(), key=lambda kv: kv[0] != "edge_index")        # stable: edge_index first
+        for key, value in ordered:
+            if key.startswith("_gsp_"):
+                continue
             out.__dict__[key] = value.to(device, non_blocking=non_blocking) if torch.is_tensor(value) else value
+            if (key == "edge_index" and non_blocking and dev.type == "cuda" and torch.is_tensor(value) and not value.is_cuda
+                    and torch.cuda.is_available()):
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream(out.__dict__[key].device))
+                out.__dict__["_gsp_edge_index_ready"] = event
+        # keep the attribute order of the source object
+        out.__dict__ = {k: out.__dict__[k] for k in list(self.__dict__.keys()) + ["_gsp_edge_index_ready"] if k in out.__dict__}
         return out
 
     def cpu(self) -> "Data":
@@ -80,7 +96,7 @@ class Data:
     def __repr__(self) -> str:
         parts = []
         for key, value in self._items():
-            if value is None:
+            if value is None or key.startswith("_gsp_"):
                 continue
             if torch.is_tensor(value):
                 parts.append(f"{key.lstrip('_')}={list(value.shape)}")

@@ -840,3 +840,20 @@ def test_gcn_norm_edge_cases():
         gcn_norm(torch.tensor([[0, 5], [1, 0]]), None, 3, device=DEV)
     with pytest.raises(ValueError):
         gcn_norm(torch.tensor([[0, 1], [1, 0]]), torch.ones(3), 2, device=DEV)
+
+
+def test_async_upload_builds_the_graph_beside_the_feature_copy():
+    """`Data.to(cuda, non_blocking=True)` from pinned memory marks the arrival of edge_index; the sparsifier builds its CSR on a
+    side stream behind that event. Results equal the synchronous path; clones do not carry the stream bookkeeping."""
+    ei, x, n = named_graph("roman_empire")
+    host = gsr_b200.Data(edge_index=torch.from_numpy(ei).pin_memory(), x=torch.from_numpy(x).pin_memory(), num_nodes=n)
+    dev_data = host.to(DEV, non_blocking=True)
+    assert hasattr(dev_data, "_gsp_edge_index_ready") and not hasattr(dev_data.clone(), "_gsp_edge_index_ready")
+    a = gsr_b200.GraphSparsifier(dev_data, DEV)
+    b = make_sparsifier(ei, n, x)
+    for m in ("jaccard", "adamic_adar", "feature_cosine"):
+        assert bits_equal(a.compute_scores(m), b.compute_scores(m)), m
+    sa, ma = a.sparsify("jaccard", 0.4, return_mask=True)
+    sb, mb = b.sparsify("jaccard", 0.4, return_mask=True)
+    assert torch.equal(ma, mb) and torch.equal(sa.edge_index.cpu(), sb.edge_index.cpu())
+    assert "gsp" not in repr(dev_data)
