@@ -54,6 +54,7 @@ PROTOTYPES = {
     "gsp_jaccard_adamic_adar": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _P]),
     "gsp_aa_node_weights": (_INT, [_P, _P, _P]),
     "gsp_aa_node_weights_from_table": (_INT, [_P, _P, _I64, _P, _P]),
+    "gsp_copy_f64": (_INT, [_P, _P, _I64, _P]),
     "gsp_jaccard_owned": (_INT, [_P, _I64, _I64, _P, _P, _P]),
     "gsp_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "gsp_jaccard_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P, _P]),

@@ -37,6 +37,18 @@ def _to_host(t: torch.Tensor) -> torch.Tensor:
     return host
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One side stream per device for the whole process: torch's caching allocator keeps a pool per stream, so a fresh stream
+    per sparsifier would strand the multi-GB score buffers of the previous one and pay cudaMalloc again."""
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    if index not in _SIDE_STREAMS:
+        _SIDE_STREAMS[index] = torch.cuda.Stream(torch.device("cuda", index))
+    return _SIDE_STREAMS[index]
+
+
 class GraphSparsifier:
     """Engine for graph sparsification via edge metric thresholding (reference core.py:24)."""
 
@@ -56,6 +68,9 @@ class GraphSparsifier:
         # --- B200 engine state (built lazily so argument validation needs no device) ---
         self._compute_device = compute_device
         self._graph: Optional[DeviceGraph] = None
+        self._side: Optional[torch.cuda.Stream] = None      # set when the graph is built beside an asynchronous upload
+        self._main: Optional[torch.cuda.Stream] = None
+        self._side_pending = False
         self._ei_dev: Optional[torch.Tensor] = None
         self._dev_scores: Dict[str, torch.Tensor] = {}
         self._xhat: Optional[torch.Tensor] = None
@@ -81,8 +96,7 @@ class GraphSparsifier:
             return torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev
         return torch.device("cuda", torch.cuda.current_device())
 
-    @property
-    def graph(self) -> DeviceGraph:
+    def _build_graph(self) -> DeviceGraph:
         if self._graph is None:
             dev = self._cuda_device()
             ei = self.data.edge_index
@@ -93,15 +107,28 @@ class GraphSparsifier:
             if ready is not None and ei.is_cuda and self._ei_dev.data_ptr() == ei.data_ptr():
                 # `Data.to(cuda, non_blocking=True)` marked the arrival of the edge list: build the CSR on a side stream that
                 # waits only for it, so the build overlaps the upload of the feature matrix queued behind it
-                main = torch.cuda.current_stream(dev)
-                side = torch.cuda.Stream(dev)
-                side.wait_event(ready)
-                with torch.cuda.stream(side):
+                self._main = torch.cuda.current_stream(dev)
+                self._side = _side_stream(dev)
+                self._side.wait_event(ready)
+                with torch.cuda.stream(self._side):
                     self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
-                self._ei_dev.record_stream(side)
-                main.wait_stream(side)
+                self._ei_dev.record_stream(self._side)
+                self._side_pending = True
             else:
                 self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
+        return self._graph
+
+    def _join_side(self) -> None:
+        """Work queued on the side stream (graph build, neighbourhood scoring started by `prefetch_scores`) becomes a
+        dependency of the caller's stream. Every access to the graph or to cached device scores goes through here."""
+        if self._side_pending:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._side_pending = False
+
+    @property
+    def graph(self) -> DeviceGraph:
+        self._build_graph()
+        self._join_side()
         return self._graph
 
     @property
@@ -149,6 +176,7 @@ class GraphSparsifier:
         """fp64 score tensor on the GPU, canonical CSR order, length nnz (cached per metric)."""
         key = self._normalize_metric_name(metric)
         if key in self._dev_scores:
+            self._join_side()
             return self._dev_scores[key]
         g = self.graph
         if key in self._score_cache:                       # injected / host-side scores: upload once
@@ -186,7 +214,16 @@ class GraphSparsifier:
         keys = [self._normalize_metric_name(m) for m in metrics]
         pending = [k for k in keys if k not in self._dev_scores and k not in self._score_cache]
         if "jaccard" in pending and "adamic_adar" in pending:
-            jac, aa = self.graph.jaccard_adamic_adar(self._aa_node_weights())
+            g = self._build_graph()
+            if self._side_pending:
+                # the graph was built beside the feature upload: the neighbourhood pass only needs the graph, so it starts on
+                # the same side stream while the features are still arriving (everything else joins before it touches either)
+                with torch.cuda.stream(self._side):
+                    jac, aa = g.jaccard_adamic_adar(g.aa_node_weights_numpy() if self.aa_weights == "numpy" else None)
+                for t in (jac, aa):
+                    t.record_stream(self._main)
+            else:
+                jac, aa = g.jaccard_adamic_adar(self._aa_node_weights())
             self._dev_scores["jaccard"], self._dev_scores["adamic_adar"] = jac, aa
         for k in keys:
             self._device_scores(k)

@@ -212,6 +212,20 @@ GSP_API int gsp_aa_node_weights(const gsp_graph* gg, double* d_node_w, void* str
     return GSP_OK;
 }
 
+// dst[i] = src[i] with SM loads: `src` may be page-locked HOST memory (unified addressing), which lets a small table reach
+// the device while the copy engine is busy with a large upload queued earlier
+__global__ void copy_f64_kernel(int64_t n, const double* __restrict__ src, double* __restrict__ dst) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+GSP_API int gsp_copy_f64(const double* src, double* d_dst, int64_t count, void* stream) {
+    GSP_REQUIRE(count >= 0 && (count == 0 || (src && d_dst)), "NULL argument");
+    if (count == 0) return GSP_OK;
+    copy_f64_kernel<<<grid_for(count, 256, 2), 256, 0, as_stream(stream)>>>(count, src, d_dst);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
 GSP_API int gsp_aa_node_weights_from_table(const gsp_graph* gg, const double* d_table, int64_t table_len, double* d_node_w,
                                            void* stream) {
     GSP_REQUIRE(gg && d_table && d_node_w, "NULL argument");

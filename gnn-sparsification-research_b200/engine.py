@@ -116,7 +116,12 @@ class DeviceGraph:
 
         if getattr(self, "_aa_table", None) is None:
             t = np.arange(self.max_degree + 1, dtype=np.float64)
-            self._aa_table = torch.from_numpy(1.0 / np.sqrt(np.maximum(np.log(t + 1), 1e-10))).to(self.device)
+            host = torch.from_numpy(1.0 / np.sqrt(np.maximum(np.log(t + 1), 1e-10))).pin_memory()
+            # fetched by a kernel from page-locked memory: the copy engine may be busy with a feature upload queued earlier
+            self._aa_table = self._empty(host.numel(), torch.float64)
+            with torch.cuda.device(self.device):
+                check(self._lib.gsp_copy_f64(ptr(host), ptr(self._aa_table), host.numel(), self._stream()))
+            self._aa_table_host = host      # stays alive until the kernel has read it (and for reuse)
         w = self._empty(self.num_nodes, torch.float64)
         with torch.cuda.device(self.device):
             check(self._lib.gsp_aa_node_weights_from_table(self._handle, ptr(self._aa_table), self._aa_table.numel(), ptr(w),

@@ -102,6 +102,10 @@ int gsp_adamic_adar(const gsp_graph* g, const double* d_node_w, int64_t e_begin,
 int gsp_aa_node_weights(const gsp_graph* g, double* d_node_w, void* stream);
 /* d_node_w[u] = d_table[deg(u)]: node weights from a caller-supplied per-degree table of max_degree + 1 entries (the host
  * evaluates the reference's NumPy expression once per distinct degree; keeps the libm-defined last bit). */
+/* d_dst[i] = src[i] by a kernel (SM loads), not by the copy engine: src may be page-locked host memory (unified
+ * addressing), so a small host-evaluated table reaches the device even while a large upload queued earlier owns the
+ * copy engine. */
+int gsp_copy_f64(const double* src, double* d_dst, int64_t count, void* stream);
 int gsp_aa_node_weights_from_table(const gsp_graph* g, const double* d_table, int64_t table_len, double* d_node_w,
                                    void* stream);
 
