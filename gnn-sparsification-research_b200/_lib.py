@@ -65,6 +65,8 @@ PROTOTYPES = {
     "gsp_gcn_norm": (_INT, [_I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gsp_target_order": (_INT, [_I64, _I64, _P, _P, _P, _P]),
     "gsp_gcn_propagate": (_INT, [_I64, _P, _P, _P, _P, _P, _I32, _I64, _P, _I64, _P]),
+    "gsp_node_triangles": (_INT, [_P, _P, _P, _P, _P]),
+    "gsp_connected_components": (_INT, [_P, _P, C.POINTER(C.c_int32), _P]),
     "gsp_degree_product": (_INT, [_P, _I64, _I64, _P, _P]),
     "gsp_featcos_normalize_f32": (_INT, [_I64, _I32, _P, _I64, _P, _I64, _P]),
     "gsp_featcos_f32": (_INT, [_P, _P, _I32, _I64, _I64, _I64, _P, _P]),

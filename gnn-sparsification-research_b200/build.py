@@ -11,7 +11,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(CSRC, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libgsp.so")
-SOURCES = ["graph.cu", "intersect.cu", "intersect_owner.cu", "featcos.cu", "select.cu", "approx_er.cu", "backbone.cu", "gcn.cu"]
+SOURCES = ["graph.cu", "intersect.cu", "intersect_owner.cu", "featcos.cu", "select.cu", "approx_er.cu", "backbone.cu", "gcn.cu", "topology.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",

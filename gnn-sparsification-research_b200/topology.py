@@ -1,0 +1,116 @@
+"""Topology metrics of a (sparsified) graph on the GPU — drop-ins for reference `src/sparsification/metrics.py:445-578`
+(`compute_topology_metrics`, `compute_topology_preservation`; NetworkX in the reference).
+
+Same names, argument (a symmetric SciPy CSR adjacency), dictionary keys and conventions: undirected edge count with a self
+loop counted once, NetworkX degrees (a loop counts twice), average local clustering coefficient, connected components and
+the share of the largest one, algebraic connectivity of the graph (of its largest component when disconnected). Triangles
+come from the intersection counts of the Jaccard pass (`gsp_node_triangles`), components from `gsp_connected_components`.
+The algebraic connectivity is a dense symmetric eigenproblem on the device (`torch.linalg.eigvalsh`) for components of up
+to `dense_limit` nodes — a convenience like the exact effective resistance, not a hand-written kernel; larger components
+report NaN (the reference's NetworkX solver is not practical there either).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict
+
+import numpy as np
+import torch
+
+from ._lib import check, ptr
+from .engine import DeviceGraph
+from .metrics import graph_from_scipy
+
+
+def node_triangles(g: DeviceGraph):
+    """(pairs int64[n], degree int32[n]): NetworkX's `t` (= 2 x triangles) and `d` of every node (self loops discounted)."""
+    _, inter = g.jaccard(return_counts=True)
+    pairs = torch.empty(g.num_nodes, dtype=torch.int64, device=g.device)
+    degree = torch.empty(g.num_nodes, dtype=torch.int32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(g._lib.gsp_node_triangles(g._handle, ptr(inter), ptr(pairs), ptr(degree), g._stream()))
+    return pairs, degree
+
+
+def clustering_coefficients(g: DeviceGraph) -> torch.Tensor:
+    """fp64[n] local clustering coefficients `t / (d (d - 1))`, 0 where undefined (nx.clustering)."""
+    pairs, degree = node_triangles(g)
+    d = degree.to(torch.float64)
+    denom = d * (d - 1.0)
+    return torch.where((pairs > 0) & (denom > 0), pairs.to(torch.float64) / denom.clamp_min(1.0), torch.zeros_like(d))
+
+
+def connected_components(g: DeviceGraph):
+    """(label int32[n] = smallest node id of each node's component, sweeps used)."""
+    label = torch.empty(g.num_nodes, dtype=torch.int32, device=g.device)
+    rounds = C.c_int32(0)
+    with torch.cuda.device(g.device):
+        check(g._lib.gsp_connected_components(g._handle, ptr(label), C.byref(rounds), g._stream()))
+    return label, int(rounds.value)
+
+
+def _algebraic_connectivity(g: DeviceGraph, label: torch.Tensor, root: int, size: int, dense_limit: int) -> float:
+    if size <= 1:
+        return 0.0
+    if size > dense_limit:
+        return float("nan")
+    indptr, indices, data, rows = g.export(with_data=True, with_rows=True)
+    nodes = torch.nonzero(label == root).flatten()
+    local = torch.full((g.num_nodes,), -1, dtype=torch.int64, device=g.device)
+    local[nodes] = torch.arange(size, device=g.device)
+    r, c = local[rows.long()], local[indices.long()]
+    keep = (r >= 0) & (c >= 0) & (r != c)
+    a = torch.zeros((size, size), dtype=torch.float64, device=g.device)
+    a[r[keep], c[keep]] = data[keep] if data is not None else 1.0
+    a = torch.maximum(a, a.T)
+    lap = torch.diag(a.sum(dim=1)) - a
+    return float(torch.linalg.eigvalsh(lap)[1])
+
+
+def topology_metrics_on_graph(g: DeviceGraph, dense_limit: int = 8192, with_connectivity: bool = True) -> Dict:
+    if not g.symmetric:
+        raise ValueError("topology metrics need a symmetric (undirected) adjacency matrix")
+    n = g.num_nodes
+    if n == 0:
+        return {"num_nodes": 0, "num_edges": 0, "avg_degree": 0.0, "clustering_coefficient": 0.0, "algebraic_connectivity": 0.0,
+                "num_connected_components": 0, "largest_component_ratio": 0.0}
+    pairs, degree = node_triangles(g)
+    loops = g.degrees().to(torch.int64) - degree.to(torch.int64)              # 1 where the row holds the node itself
+    num_loops = int(loops.sum())
+    num_edges = int(degree.sum(dtype=torch.int64)) // 2 + num_loops
+    avg_degree = float((degree.to(torch.int64) + 2 * loops).sum()) / n
+    d = degree.to(torch.float64)
+    denom = d * (d - 1.0)
+    c = torch.where((pairs > 0) & (denom > 0), pairs.to(torch.float64) / denom.clamp_min(1.0), torch.zeros_like(d))
+    label, _ = connected_components(g)
+    sizes = torch.bincount(label.long(), minlength=n)
+    num_components = int((sizes > 0).sum())
+    largest = int(sizes.max())
+    out = {
+        "num_nodes": n, "num_edges": num_edges, "avg_degree": avg_degree,
+        "clustering_coefficient": float(c.sum()) / n, "algebraic_connectivity": 0.0,
+        "num_connected_components": num_components, "largest_component_ratio": largest / n,
+    }
+    if with_connectivity and n > 1:
+        out["algebraic_connectivity"] = _algebraic_connectivity(g, label, int(sizes.argmax()), largest, dense_limit)
+    return out
+
+
+def compute_topology_metrics(adj, dense_limit: int = 8192) -> Dict:
+    """reference metrics.py:445-520."""
+    return topology_metrics_on_graph(graph_from_scipy(adj), dense_limit=dense_limit)
+
+
+def compute_topology_preservation(original_adj, sparse_adj) -> Dict:
+    """reference metrics.py:523-578."""
+    orig, sparse = compute_topology_metrics(original_adj), compute_topology_metrics(sparse_adj)
+    return {
+        "edge_retention": sparse["num_edges"] / orig["num_edges"] if orig["num_edges"] > 0 else 0.0,
+        "clustering_preservation": (sparse["clustering_coefficient"] / orig["clustering_coefficient"]
+                                    if orig["clustering_coefficient"] > 0 else 1.0),
+        "connectivity_preservation": (sparse["algebraic_connectivity"] / orig["algebraic_connectivity"]
+                                      if orig["algebraic_connectivity"] > 0 else 0.0),
+        "component_change": sparse["num_connected_components"] - orig["num_connected_components"],
+        "original_metrics": orig,
+        "sparse_metrics": sparse,
+    }

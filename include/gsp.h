@@ -264,6 +264,18 @@ int gsp_gcn_propagate(int64_t num_nodes, const int64_t* d_indptr, const int64_t*
                       const float* d_weight, const float* d_x, int32_t dim, int64_t ldx, float* d_out, int64_t ldo,
                       void* stream);
 
+/* ---- topology of the (sparsified) graph ---------------------------------------------
+ * Building blocks of reference src/sparsification/metrics.py:445-520 `compute_topology_metrics` (NetworkX there).
+ * Symmetric graphs only (GSP_ERR_UNSUPPORTED otherwise).
+ * gsp_node_triangles: d_inter = the int32[nnz] intersection counts of gsp_jaccard; d_pairs[v] (int64) = number of
+ * ordered neighbour pairs of v that are adjacent = 2 * triangles through v, d_degree[v] (int32) = neighbours other
+ * than v itself — the t and d of nx.clustering: c_v = t / (d (d - 1)) (metrics.py:468 nx.average_clustering).
+ * Self loops are discounted the way NetworkX does (a node is not its own neighbour). */
+int gsp_node_triangles(const gsp_graph* g, const int32_t* d_inter, int64_t* d_pairs, int32_t* d_degree, void* stream);
+/* d_label[v] (int32) = smallest node id of v's connected component (metrics.py:471 nx.connected_components):
+ * min-label hooking + pointer jumping; *rounds_out (host, optional) = sweeps used. Reads one flag back per sweep. */
+int gsp_connected_components(const gsp_graph* g, int32_t* d_label, int32_t* rounds_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,8 @@
 oracle and the committed golden fixtures. Bars (BASELINE.json north_star): Jaccard counts, every score
 built from integer/ordered-fp work, and all keep-masks bit-exact; ApproxER <= 1e-4 relative with
 >= 99.9 % kept-set agreement."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sparse
@@ -857,3 +859,64 @@ def test_async_upload_builds_the_graph_beside_the_feature_copy():
     sb, mb = b.sparsify("jaccard", 0.4, return_mask=True)
     assert torch.equal(ma, mb) and torch.equal(sa.edge_index.cpu(), sb.edge_index.cpu())
     assert "gsp" not in repr(dev_data)
+
+
+# ----------------------------------------------------------------------------- topology metrics
+def test_topology_metrics_against_reference_goldens():
+    """compute_topology_metrics on the GPU against what the live reference (NetworkX) returned for nine graphs — triangles
+    from the Jaccard counts, min-label components, dense Laplacian eigenvalue — counts exact, means 1e-12, eigenvalue 1e-6."""
+    import json
+
+    from gsr_b200.topology import compute_topology_metrics, compute_topology_preservation
+    from oracle.make_topology_golden import adjacency, graphs
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "topology_metrics.json")))
+    adjs = {}
+    for name, ei, n in graphs():
+        adj = adjacency(ei, n)
+        adj.data[:] = 1.0
+        adjs[name] = adj
+        got, want = compute_topology_metrics(adj), gold[name]
+        assert set(got) == set(want)
+        for k in ("num_nodes", "num_edges", "num_connected_components"):
+            assert got[k] == want[k], (name, k, got[k], want[k])
+        for k in ("avg_degree", "clustering_coefficient", "largest_component_ratio"):
+            assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (name, k, got[k], want[k])
+        assert abs(got["algebraic_connectivity"] - want["algebraic_connectivity"]) <= 1e-6 * max(1.0, want["algebraic_connectivity"]), name
+    pres = compute_topology_preservation(adjs["karate_unsorted"], adjs["karate_unsorted"])
+    assert pres["edge_retention"] == 1.0 and pres["clustering_preservation"] == 1.0 and pres["component_change"] == 0
+
+
+def test_topology_building_blocks_on_larger_graphs():
+    """Per-node triangle pairs / degrees and component labels against SciPy on a hub graph, a 2^15-node R-MAT and a long chain
+    (components must converge in a few sweeps despite a diameter in the thousands)."""
+    from scipy.sparse.csgraph import connected_components as cc_ref
+
+    from gsr_b200.topology import connected_components, node_triangles
+    from oracle import topology_port
+
+    chain = chain_with_shortcuts(20000, 0, seed=1)
+    chain = chain[:, (chain[0] != 9999) & (chain[1] != 9999)]          # cut the path: two long components + one isolated node
+    cases = [hub_graph(n=12000, hub_deg=9000, extra=30000, seed=8), (rmat_graph(1 << 15, 16 << 15, 15, seed=21), 1 << 15),
+             (chain, 20000)]
+    for ei, n in cases:
+        g = make_sparsifier(ei, n).graph
+        adj = sparse.csr_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n))
+        adj.data[:] = 1.0
+        off = adj - sparse.diags(adj.diagonal())
+        off.eliminate_zeros()
+        pairs, degree = node_triangles(g)
+        assert np.array_equal(degree.cpu().numpy(), np.asarray(off.sum(axis=1)).ravel().astype(np.int32))
+        assert np.array_equal(pairs.cpu().numpy(), np.asarray((off @ off).multiply(off).sum(axis=1)).ravel().astype(np.int64))
+        label, rounds = connected_components(g)
+        num, ref_labels = cc_ref(adj, directed=False)
+        lab = label.cpu().numpy()
+        assert len(np.unique(lab)) == num and rounds <= 40
+        first = np.full(num, n, dtype=np.int64)
+        np.minimum.at(first, ref_labels, np.arange(n))
+        assert np.array_equal(lab, first[ref_labels])                    # label = smallest node id of the component
+        want = topology_port.compute_topology_metrics(adj, with_connectivity=False)
+        from gsr_b200.topology import topology_metrics_on_graph
+        got = topology_metrics_on_graph(g, with_connectivity=False)
+        assert got["num_edges"] == want["num_edges"] and got["num_connected_components"] == want["num_connected_components"]
+        assert abs(got["clustering_coefficient"] - want["clustering_coefficient"]) <= 1e-12

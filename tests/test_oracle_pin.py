@@ -4,6 +4,7 @@
   oracle/make_golden.py) — runs everywhere, including the GPU box;
 * against the live reference imported from /root/reference — build container only.
 """
+import os
 import sys
 
 import numpy as np
@@ -177,3 +178,31 @@ def test_metric_backbone_oracle_matches_live_reference(shape):
         assert bits_equal(co.scores_to_cost(s), cost)
         _, stats = sp.sparsify_metric_backbone(metric)
         assert np.array_equal(co.metric_backbone_mask(ei, n, cost), stats["keep_mask"]), metric
+
+
+def test_topology_port_matches_goldens_and_live_reference():
+    """oracle/topology_port.py against tests/golden/topology_metrics.json (live reference, NetworkX) and, in the build
+    container, against the reference function itself."""
+    import json
+
+    from oracle import topology_port
+    from oracle.make_topology_golden import adjacency, graphs
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "topology_metrics.json")))
+    live = None
+    if ref_loader.available():
+        ref = ref_loader.load()
+        live = __import__(ref.__name__ + ".metrics", fromlist=["compute_topology_metrics"]).compute_topology_metrics
+    seen = 0
+    for name, ei, n in graphs():
+        adj = adjacency(ei, n)
+        adj.data[:] = 1.0
+        got = topology_port.compute_topology_metrics(adj)
+        for want in ([gold[name]] + ([live(adj)] if live is not None and n <= 400 else [])):
+            for k in ("num_nodes", "num_edges", "num_connected_components"):
+                assert got[k] == want[k], (name, k)
+            for k in ("avg_degree", "clustering_coefficient", "largest_component_ratio"):
+                assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (name, k)
+            assert abs(got["algebraic_connectivity"] - want["algebraic_connectivity"]) <= 1e-6 * max(1.0, want["algebraic_connectivity"]), name
+        seen += 1
+    assert seen == len(gold) == 9
