@@ -70,6 +70,15 @@ def test_no_cpu_fallback():
     import scipy.sparse as sparse
     with pytest.raises(_lib.GspError, match="no CPU fallback"):
         gsr_b200.calculate_jaccard_scores(sparse.csr_matrix(np.array([[0, 1], [1, 0]])))
+    with pytest.raises(_lib.GspError, match="no CPU fallback"):
+        sp.prefetch_scores(["jaccard", "adamic_adar"])
+    from gsr_b200 import gcn, topology
+    with pytest.raises(_lib.GspError, match="no CPU fallback"):
+        gcn.gcn_norm(torch.tensor([[0, 1], [1, 0]]), None, 2)
+    with pytest.raises(_lib.GspError, match="no CPU fallback"):
+        gcn.GcnPropagation(torch.tensor([[0, 1], [1, 0]]), None, 2)
+    with pytest.raises(_lib.GspError, match="no CPU fallback"):
+        topology.compute_topology_metrics(sparse.csr_matrix(np.array([[0, 1], [1, 0]])))
 
 
 def test_product_never_imports_the_oracle():
