@@ -11,6 +11,7 @@ from .metrics import (
     calculate_jaccard_scores,
 )
 from .metric_backbone import compute_metric_backbone
+from .topology import compute_geodesic_preservation, compute_topology_metrics, compute_topology_preservation
 from .random import precompute_random_scores, random_sparsify
 
 __all__ = [
@@ -21,6 +22,9 @@ __all__ = [
     "calculate_effective_resistance_scores",
     "calculate_approx_effective_resistance_scores",
     "calculate_feature_cosine_scores",
+    "compute_geodesic_preservation",
+    "compute_topology_metrics",
+    "compute_topology_preservation",
     "compute_metric_backbone",
     "precompute_random_scores",
     "random_sparsify",

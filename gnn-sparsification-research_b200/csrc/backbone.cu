@@ -16,12 +16,15 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / kWarp;
 constexpr int kCheckEvery = 4;   // sweeps between host reads of the "changed" flag
 
-__global__ void sssp_init_kernel(int64_t n, int64_t src_begin, int S, double* __restrict__ dist) {
+// column c starts from node src_begin + c, or from sources[c] when an explicit source list is given
+__global__ void sssp_init_kernel(int64_t n, int64_t src_begin, const int32_t* __restrict__ sources, int S,
+                                 double* __restrict__ dist) {
     const int64_t total = n * (int64_t)S;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = i / S;
         const int c = (int)(i - v * S);
-        dist[i] = (v == src_begin + c) ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
+        const int64_t src = sources ? (int64_t)sources[c] : src_begin + c;
+        dist[i] = (v == src) ? 0.0 : __longlong_as_double(0x7ff0000000000000ll);
     }
 }
 
@@ -66,23 +69,19 @@ sssp_relax_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
 
 using namespace gsp;
 
-GSP_API int gsp_sssp_batch(const gsp_graph* gg, const double* d_weights, int64_t src_begin, int32_t src_count,
-                           double* d_dist, int32_t max_rounds, int32_t* rounds_out, void* stream) {
-    GSP_REQUIRE(gg != nullptr, "graph is NULL");
-    const Graph* g = reinterpret_cast<const Graph*>(gg);
-    GSP_REQUIRE(src_begin >= 0 && src_count >= 0 && src_begin + src_count <= g->n, "source range outside [0, num_nodes]");
+static int sssp_run(const Graph* g, const double* d_weights, int64_t src_begin, const int32_t* d_sources, int32_t src_count,
+                    double* d_dist, int32_t max_rounds, int32_t* rounds_out, cudaStream_t s) {
     GSP_REQUIRE(max_rounds >= 1, "max_rounds must be >= 1");
     if (rounds_out) *rounds_out = 0;
     if (src_count == 0 || g->n == 0) return GSP_OK;
     GSP_REQUIRE(d_dist && (g->nnz == 0 || d_weights), "NULL argument");
     if (!g->symmetric) {
-        set_error("gsp_sssp_batch needs a symmetric (undirected) graph");
+        set_error("batched shortest paths need a symmetric (undirected) graph");
         return GSP_ERR_UNSUPPORTED;
     }
-    cudaStream_t s = as_stream(stream);
     const int64_t n = g->n;
     const int S = src_count;
-    sssp_init_kernel<<<grid_for(n * (int64_t)S, 256), 256, 0, s>>>(n, src_begin, S, d_dist);
+    sssp_init_kernel<<<grid_for(n * (int64_t)S, 256), 256, 0, s>>>(n, src_begin, d_sources, S, d_dist);
     GSP_CHECK_LAUNCH();
     Scratch<int> changed;
     GSP_CUDA_TRY(changed.alloc(1, s));
@@ -107,4 +106,20 @@ GSP_API int gsp_sssp_batch(const gsp_graph* gg, const double* d_weights, int64_t
     }
     if (rounds_out) *rounds_out = rounds;
     return GSP_OK;
+}
+
+GSP_API int gsp_sssp_batch(const gsp_graph* gg, const double* d_weights, int64_t src_begin, int32_t src_count,
+                           double* d_dist, int32_t max_rounds, int32_t* rounds_out, void* stream) {
+    GSP_REQUIRE(gg != nullptr, "graph is NULL");
+    const Graph* g = reinterpret_cast<const Graph*>(gg);
+    GSP_REQUIRE(src_begin >= 0 && src_count >= 0 && src_begin + src_count <= g->n, "source range outside [0, num_nodes]");
+    return sssp_run(g, d_weights, src_begin, nullptr, src_count, d_dist, max_rounds, rounds_out, as_stream(stream));
+}
+
+GSP_API int gsp_sssp_sources(const gsp_graph* gg, const double* d_weights, const int32_t* d_sources, int32_t src_count,
+                             double* d_dist, int32_t max_rounds, int32_t* rounds_out, void* stream) {
+    GSP_REQUIRE(gg != nullptr, "graph is NULL");
+    GSP_REQUIRE(src_count >= 0 && (src_count == 0 || d_sources != nullptr), "source list is NULL");
+    return sssp_run(reinterpret_cast<const Graph*>(gg), d_weights, 0, d_sources, src_count, d_dist, max_rounds, rounds_out,
+                    as_stream(stream));
 }

@@ -1,5 +1,6 @@
-"""Topology metrics of a (sparsified) graph on the GPU — drop-ins for reference `src/sparsification/metrics.py:445-578`
-(`compute_topology_metrics`, `compute_topology_preservation`; NetworkX in the reference).
+"""Topology metrics of a (sparsified) graph on the GPU — drop-ins for reference `src/sparsification/metrics.py:361-578`
+(`compute_geodesic_preservation`, `compute_topology_metrics`, `compute_topology_preservation`; NetworkX in the reference,
+SURVEY §8f-4).
 
 Same names, argument (a symmetric SciPy CSR adjacency), dictionary keys and conventions: undirected edge count with a self
 loop counted once, NetworkX degrees (a loop counts twice), average local clustering coefficient, connected components and
@@ -113,4 +114,85 @@ def compute_topology_preservation(original_adj, sparse_adj) -> Dict:
         "component_change": sparse["num_connected_components"] - orig["num_connected_components"],
         "original_metrics": orig,
         "sparse_metrics": sparse,
+    }
+
+
+def hop_distances(g: DeviceGraph, sources, scratch_bytes: float = 16e9) -> torch.Tensor:
+    """fp64 [len(sources), n] hop counts (inf = unreachable) from the given source nodes: batched (min,+) relaxation with unit
+    edge lengths (`gsp_sssp_sources`), the device form of the reference's repeated `nx.shortest_path_length` calls."""
+    n = g.num_nodes
+    src = torch.as_tensor(list(sources), dtype=torch.int32, device=g.device)
+    out = torch.empty((src.numel(), n), dtype=torch.float64, device=g.device)
+    if src.numel() == 0 or n == 0:
+        return out
+    if int(src.min()) < 0 or int(src.max()) >= n:
+        raise ValueError("source ids outside [0, num_nodes)")
+    ones = torch.ones(max(g.nnz, 1), dtype=torch.float64, device=g.device)
+    batch = int(max(1, min(src.numel(), scratch_bytes // (8 * max(n, 1)))))
+    rounds = C.c_int32(0)
+    for s0 in range(0, src.numel(), batch):
+        s1 = min(src.numel(), s0 + batch)
+        dist = torch.empty((n, s1 - s0), dtype=torch.float64, device=g.device)       # [n, S]: sources contiguous
+        with torch.cuda.device(g.device):
+            check(g._lib.gsp_sssp_sources(g._handle, ptr(ones), ptr(src[s0:s1].contiguous()), s1 - s0, ptr(dist), max(n, 1),
+                                          C.byref(rounds), g._stream()))
+        out[s0:s1] = dist.T
+        del dist
+    return out
+
+
+def _undirected_pattern_graph(adj) -> DeviceGraph:
+    import scipy.sparse as sp
+
+    pat = sp.csr_matrix(adj) != 0
+    pat = sp.csr_matrix((pat + pat.T).astype(np.float64))       # NetworkX builds an undirected graph from either direction
+    pat.data[:] = 1.0
+    return graph_from_scipy(pat)
+
+
+def compute_geodesic_preservation(original_adj, sparse_adj, n_samples: int = 500, seed: int = 42) -> Dict:
+    """reference metrics.py:361-442: share of sampled node pairs whose hop distance survives sparsification. The pair sample is
+    drawn on the host exactly like the reference does (NumPy PCG64: the stream is observable behaviour); the distances
+    come from the device."""
+    n = original_adj.shape[0]
+    rng = np.random.default_rng(seed)
+    pairs = set()
+    attempts = 0
+    while len(pairs) < n_samples and attempts < n_samples * 10:
+        u, v = rng.integers(0, n, size=2)
+        if u != v:
+            pairs.add((min(u, v), max(u, v)))
+        attempts += 1
+    pairs = list(pairs)
+    preserved = increased = disconnected = 0
+    increases = []
+    if pairs:
+        sources = sorted({int(u) for u, _ in pairs})
+        column = {u: i for i, u in enumerate(sources)}
+        rows = torch.tensor([column[int(u)] for u, _ in pairs], dtype=torch.int64)
+        cols = torch.tensor([int(v) for _, v in pairs], dtype=torch.int64)
+        def sampled(adj):
+            d = hop_distances(_undirected_pattern_graph(adj), sources)
+            return d[rows.to(d.device), cols.to(d.device)].cpu().numpy()
+
+        d_orig, d_sparse = sampled(original_adj), sampled(sparse_adj)
+        for a, b in zip(d_orig, d_sparse):
+            if np.isinf(a):
+                continue                         # already disconnected in the original graph
+            if np.isinf(b):
+                disconnected += 1
+            elif b == a:
+                preserved += 1
+            else:
+                increased += 1
+                increases.append(int(b - a))
+    total_valid = preserved + increased + disconnected
+    return {
+        "preservation_ratio": preserved / total_valid if total_valid > 0 else 0.0,
+        "pairs_tested": len(pairs),
+        "preserved_count": preserved,
+        "increased_count": increased,
+        "disconnected_count": disconnected,
+        "avg_distance_increase": np.mean(increases) if increases else 0.0,
+        "max_distance_increase": max(increases) if increases else 0,
     }

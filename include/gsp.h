@@ -189,6 +189,11 @@ int gsp_er_finalize(double* d_score, int64_t count, void* stream);
  * Synchronises the stream every few sweeps. */
 int gsp_sssp_batch(const gsp_graph* g, const double* d_weights, int64_t src_begin, int32_t src_count, double* d_dist,
                    int32_t max_rounds, int32_t* rounds_out, void* stream);
+/* Same relaxation from an explicit list of source nodes (d_sources int32[src_count], ids in [0, num_nodes)); column c of
+ * d_dist holds the distances from d_sources[c]. With unit weights these are hop counts: the sampled
+ * nx.shortest_path_length calls of reference metrics.py:361-442 (compute_geodesic_preservation). */
+int gsp_sssp_sources(const gsp_graph* g, const double* d_weights, const int32_t* d_sources, int32_t src_count,
+                     double* d_dist, int32_t max_rounds, int32_t* rounds_out, void* stream);
 
 /* ---- selection ---------------------------------------------------------------------------------
  * Radix-histogram select with stable (score, position) tie-breaking — replaces the full argsort of

@@ -1,5 +1,5 @@
-"""TEST INFRASTRUCTURE — tests/golden/topology_metrics.json from the LIVE reference (`compute_topology_metrics`,
-reference src/sparsification/metrics.py:445-520, NetworkX) for the symmetric golden fixture graphs and three generated
+"""TEST INFRASTRUCTURE — tests/golden/topology_metrics.json and geodesic_preservation.json from the LIVE reference
+(`compute_topology_metrics`, `compute_geodesic_preservation`, reference src/sparsification/metrics.py:361-520, NetworkX) for the symmetric golden fixture graphs and three generated
 ones. Run in the build container:   python oracle/make_topology_golden.py"""
 from __future__ import annotations
 
@@ -38,9 +38,28 @@ def adjacency(ei, n):
     return sp.csr_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n))
 
 
+GEODESIC_CASES = (("karate_unsorted", 200), ("rmat_300", 200), ("chain_400", 150), ("rmat_2000", 300), ("blocks_with_loops", 120))
+
+
+def thinned(ei):
+    """Deterministic sub-graph: drops every undirected edge whose endpoints hash to 0 mod 3 (keeps symmetry)."""
+    lo, hi = np.minimum(ei[0], ei[1]), np.maximum(ei[0], ei[1])
+    return ei[:, (lo * 7 + hi * 13) % 3 != 0]
+
+
 def main():
     ref = ref_loader.load()
     metrics = __import__(ref.__name__ + ".metrics", fromlist=["compute_topology_metrics"])
+    geo = {}
+    by_name = {name: (ei, n) for name, ei, n in graphs()}
+    for name, samples in GEODESIC_CASES:
+        ei, n = by_name[name]
+        m = metrics.compute_geodesic_preservation(adjacency(ei, n), adjacency(thinned(ei), n), n_samples=samples, seed=42)
+        geo[name] = {k: (float(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
+        geo[name]["n_samples"] = samples
+        print("geodesic", name, geo[name])
+    with open(os.path.join(ROOT, "tests", "golden", "geodesic_preservation.json"), "w") as f:
+        json.dump(geo, f, indent=1, sort_keys=True)
     out = {}
     for name, ei, n in graphs():
         adj = adjacency(ei, n)

@@ -68,3 +68,53 @@ def compute_topology_preservation(original_adj, sparse_adj) -> dict:
         "component_change": s["num_connected_components"] - o["num_connected_components"],
         "original_metrics": o, "sparse_metrics": s,
     }
+
+
+def sample_pairs(n: int, n_samples: int, seed: int):
+    """The reference's pair sampling (metrics.py:388-402): PCG64 draws until `n_samples` distinct unordered pairs."""
+    rng = np.random.default_rng(seed)
+    pairs = set()
+    attempts = 0
+    while len(pairs) < n_samples and attempts < n_samples * 10:
+        u, v = rng.integers(0, n, size=2)
+        if u != v:
+            pairs.add((min(u, v), max(u, v)))
+        attempts += 1
+    return list(pairs)
+
+
+def compute_geodesic_preservation(original_adj, sparse_adj, n_samples: int = 500, seed: int = 42) -> dict:
+    """metrics.py:361-442 with SciPy breadth-first distances in place of nx.shortest_path_length (hop counts)."""
+    from scipy.sparse.csgraph import shortest_path
+
+    n = original_adj.shape[0]
+    pairs = sample_pairs(n, n_samples, seed)
+    sources = sorted({int(u) for u, _ in pairs})
+    col = {u: i for i, u in enumerate(sources)}
+
+    def hops(adj):
+        pat = sp.csr_matrix(adj) != 0
+        pat = (pat + pat.T).astype(np.float64)
+        return shortest_path(pat, method="D", directed=False, unweighted=True, indices=sources) if sources else np.zeros((0, n))
+
+    d_o, d_s = hops(original_adj), hops(sparse_adj)
+    preserved = increased = disconnected = 0
+    inc = []
+    for u, v in pairs:
+        a = d_o[col[int(u)], int(v)]
+        if np.isinf(a):
+            continue
+        b = d_s[col[int(u)], int(v)]
+        if np.isinf(b):
+            disconnected += 1
+        elif b == a:
+            preserved += 1
+        else:
+            increased += 1
+            inc.append(int(b - a))
+    total = preserved + increased + disconnected
+    return {
+        "preservation_ratio": preserved / total if total > 0 else 0.0, "pairs_tested": len(pairs), "preserved_count": preserved,
+        "increased_count": increased, "disconnected_count": disconnected,
+        "avg_distance_increase": float(np.mean(inc)) if inc else 0.0, "max_distance_increase": max(inc) if inc else 0,
+    }

@@ -920,3 +920,30 @@ def test_topology_building_blocks_on_larger_graphs():
         got = topology_metrics_on_graph(g, with_connectivity=False)
         assert got["num_edges"] == want["num_edges"] and got["num_connected_components"] == want["num_connected_components"]
         assert abs(got["clustering_coefficient"] - want["clustering_coefficient"]) <= 1e-12
+
+
+def test_geodesic_preservation_against_reference_goldens():
+    """compute_geodesic_preservation: host pair sampling as in the reference, hop distances from gsp_sssp_sources; every count
+    equals what the live reference (NetworkX) returned, including pairs that the thinned graph disconnects."""
+    import json
+
+    from gsr_b200 import compute_geodesic_preservation
+    from gsr_b200.topology import hop_distances
+    from oracle.make_topology_golden import GEODESIC_CASES, adjacency, graphs, thinned
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "geodesic_preservation.json")))
+    by_name = {name: (ei, n) for name, ei, n in graphs()}
+    for name, samples in GEODESIC_CASES:
+        ei, n = by_name[name]
+        got = compute_geodesic_preservation(adjacency(ei, n), adjacency(thinned(ei), n), n_samples=samples, seed=42)
+        assert set(got) == set(gold[name]) - {"n_samples"}
+        for k, v in got.items():
+            assert abs(v - gold[name][k]) <= 1e-12, (name, k, v, gold[name][k])
+    # hop distances themselves against SciPy on a chain with shortcuts (long shortest paths) from scattered sources
+    from scipy.sparse.csgraph import shortest_path
+
+    ei = chain_with_shortcuts(3000, 25, seed=4)
+    g = make_sparsifier(ei, 3000).graph
+    sources = [0, 17, 1499, 2999, 512]
+    want = shortest_path(adjacency(ei, 3000), method="D", directed=False, unweighted=True, indices=sources)
+    assert np.array_equal(hop_distances(g, sources).cpu().numpy(), want)

@@ -206,3 +206,18 @@ def test_topology_port_matches_goldens_and_live_reference():
             assert abs(got["algebraic_connectivity"] - want["algebraic_connectivity"]) <= 1e-6 * max(1.0, want["algebraic_connectivity"]), name
         seen += 1
     assert seen == len(gold) == 9
+
+
+def test_geodesic_port_matches_goldens():
+    import json
+
+    from oracle import topology_port
+    from oracle.make_topology_golden import GEODESIC_CASES, adjacency, graphs, thinned
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "geodesic_preservation.json")))
+    by_name = {name: (ei, n) for name, ei, n in graphs()}
+    for name, samples in GEODESIC_CASES:
+        ei, n = by_name[name]
+        got = topology_port.compute_geodesic_preservation(adjacency(ei, n), adjacency(thinned(ei), n), n_samples=samples, seed=42)
+        for k, v in got.items():
+            assert abs(v - gold[name][k]) <= 1e-12, (name, k)
