@@ -136,3 +136,15 @@ def test_profiles_traffic_record_is_well_formed():
     assert t["workload"] == {"scale": 24, "edge_factor": 16, "dim": 128, "n_gpus": 1}
     for k in ("jaccard", "adamic_adar"):
         assert 1e10 < t[k]["dram_bytes_per_launch"] < 1e12
+
+
+def test_data_container_semantics_on_the_host():
+    """`Data.to` / `clone` keep the attribute order and never leak the upload bookkeeping (host-only check; the asynchronous
+    CUDA path is covered by the GPU tests)."""
+    d = gsr_b200.Data(x=torch.randn(4, 3), edge_index=torch.tensor([[0, 1], [1, 0]]), num_nodes=4, note="kept")
+    moved = d.to("cpu", non_blocking=True)
+    assert list(moved.__dict__) == list(d.__dict__) and moved.note == "kept" and moved.num_nodes == 4
+    assert not any(k.startswith("_gsp_") for k in moved.__dict__)                 # events only for uploads to a CUDA device
+    moved._gsp_edge_index_ready = object()
+    assert not hasattr(moved.clone(), "_gsp_edge_index_ready") and "gsp" not in repr(moved)
+    assert torch.equal(moved.clone().edge_index, d.edge_index) and moved.clone().edge_index is not moved.edge_index

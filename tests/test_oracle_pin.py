@@ -221,3 +221,39 @@ def test_geodesic_port_matches_goldens():
         got = topology_port.compute_geodesic_preservation(adjacency(ei, n), adjacency(thinned(ei), n), n_samples=samples, seed=42)
         for k, v in got.items():
             assert abs(v - gold[name][k]) <= 1e-12, (name, k)
+
+
+def test_pyg_port_matches_dense_normalised_adjacency():
+    """oracle/pyg_port.py (restatement of torch_geometric's gcn_norm + propagate; the library itself is not installed, so this
+    is the only pin it has) against a dense D^-1/2 (A + I') D^-1/2 built independently, with self loops that keep their
+    weight, duplicate edges and isolated nodes."""
+    from oracle import pyg_port
+
+    rng = np.random.default_rng(0)
+    n = 25
+    ei = np.vstack([rng.integers(0, 20, 120), rng.integers(0, 20, 120)])          # nodes 20..24 isolated, some loops/duplicates
+    w = (rng.random(120) + 0.1).astype(np.float32)
+    out_ei, out_w = pyg_port.gcn_norm(ei, w, n)
+    mask = ei[0] != ei[1]
+    assert np.array_equal(out_ei[:, : mask.sum()], ei[:, mask])                   # non-loop edges first, in order
+    assert np.array_equal(out_ei[:, mask.sum():], np.vstack([np.arange(n)] * 2))  # then one loop per node
+    dense = np.zeros((n, n))
+    for (r, c), v in zip(ei[:, mask].T, w[mask]):
+        dense[c, r] += v                                                          # aggregation at the target
+    loop = np.ones(n)
+    for (r, _), v in zip(ei[:, ~mask].T, w[~mask]):
+        loop[r] = v                                                               # the last loop edge of a node wins
+    dense += np.diag(loop)
+    deg = dense.sum(axis=1)
+    want = dense / np.sqrt(deg)[:, None] / np.sqrt(deg)[None, :]
+    got = np.zeros((n, n))
+    for (r, c), v in zip(out_ei.T, out_w):
+        got[c, r] += v
+    assert np.abs(got - want).max() < 5e-7
+    x = rng.standard_normal((n, 6)).astype(np.float32)
+    assert np.abs(pyg_port.propagate(out_ei, out_w, x, n) - want @ x).max() < 5e-6
+    # unweighted graph without loops: weights are exactly 1 / sqrt((d_u + 1)(d_v + 1)) up to fp32 rounding
+    ring = np.vstack([np.arange(8), (np.arange(8) + 1) % 8])
+    ring = np.hstack([ring, ring[::-1]])
+    _, rw = pyg_port.gcn_norm(ring, None, 8)
+    assert np.allclose(rw, 1.0 / 3.0, rtol=2e-7)
