@@ -84,6 +84,7 @@ PROTOTYPES = {
     "gsp_select_count_ties": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "gsp_select_write_mask": (_INT, [_P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
     "gsp_select_mask": (_INT, [_P, _I64, _I64, _INT, _P, _INT, _P, _P]),
+    "gsp_select_compact": (_INT, [_P, _I64, _I64, _INT, _P, _I64, _P, _P, _I64, _P, _INT, _P, _P]),
     "gsp_degree_aware_guarantee": (_INT, [_P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "gsp_compact_edges": (_INT, [_P, _I64, _I64, _P, _P, _INT, _P, _I64, _P, _P, _P]),
 }

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import DeviceGraph, compact_edges, degree_aware_guarantee, select_mask
+from .engine import DeviceGraph, compact_edges, degree_aware_guarantee, select_compact, select_mask
 
 
 def _to_host(t: torch.Tensor) -> torch.Tensor:
@@ -58,7 +58,15 @@ class GraphSparsifier:
     }
     _DISTANCE_METRICS = {"effective_resistance", "approx_effective_resistance"}
 
-    def __init__(self, data, device: str, compute_device: Optional[str] = None) -> None:
+    def __new__(cls, data=None, device=None, compute_device=None, group=None, **kwargs):
+        # extension: `group=` (a torch.distributed process group, one process per GPU) returns the sharded engine with
+        # the same method API (sharded_sparsifier.py)
+        if cls is GraphSparsifier and group is not None:
+            from .sharded_sparsifier import ShardedGraphSparsifier
+            return super().__new__(ShardedGraphSparsifier)
+        return super().__new__(cls)
+
+    def __init__(self, data, device: str, compute_device: Optional[str] = None, group=None) -> None:
         self.data = data
         self.device = device
         self.num_nodes = data.num_nodes
@@ -288,15 +296,41 @@ class GraphSparsifier:
             select_mask(scores, take, keep_lowest, out=mask[:nnz])
         return mask, take
 
+    def _take(self, num_keep: int, keep_lowest: bool, nnz: int) -> int:
+        """How many of the `nnz` scored positions the reference's slices keep (core.py:232-237): `order[:k]`,
+        `order[-k:]` — and `order[-0:]` is the whole array."""
+        if not keep_lowest and num_keep == 0:
+            return nnz
+        return min(num_keep, nnz)
+
+    def _select_finish(self, scores: torch.Tensor, take: int, keep_lowest: bool, return_mask: bool, with_weights: bool = False):
+        """Boundary search, keep-mask, `edge_index[:, mask]` and (optionally) the "-W" weights in one library call
+        (`gsp_select_compact`); positions >= nnz (duplicate edges) are never kept (reference core.py:239-245)."""
+        nnz = scores.numel()
+        mask = None
+        if return_mask:
+            mask = (torch.zeros if nnz < self.num_edges or take == 0 else torch.empty)(self.num_edges, dtype=torch.uint8,
+                                                                                       device=scores.device)
+        weights = None
+        if take > 0:
+            kept, weights, _ = select_compact(scores, take, keep_lowest, self._ei_dev, mask, with_weights, invert_weights=keep_lowest)
+        else:
+            kept = torch.empty((2, 0), dtype=torch.int64, device=scores.device)
+            weights = torch.empty(0, dtype=torch.float32, device=scores.device) if with_weights else None
+        sparse_data = self.data.clone()
+        sparse_data.edge_index = kept.to(self.device)
+        host_mask = _to_host(mask.view(torch.bool)) if return_mask else None   # 0/1 bytes reinterpreted, no conversion pass
+        return sparse_data, weights, host_mask
+
     def sparsify(self, metric: str, retention_ratio: float, return_mask: bool = False, keep_lowest: bool = False):
         """Keep the top (or bottom) `int(num_edges * retention_ratio)` edges by score (reference core.py:193-249)."""
         self._check_ratio(retention_ratio)
         if retention_ratio == 1.0:
             return self._full(return_mask)
         scores = self._device_scores(metric)
-        num_keep = int(self.num_edges * retention_ratio)
-        mask, kept = self._threshold_mask(scores, num_keep, keep_lowest)
-        return self._finish(mask, kept, return_mask)
+        take = self._take(int(self.num_edges * retention_ratio), keep_lowest, scores.numel())
+        sparse_data, _, mask = self._select_finish(scores, take, keep_lowest, return_mask)
+        return (sparse_data, mask) if return_mask else sparse_data
 
     def sparsify_with_weights(self, metric: str, retention_ratio: float, keep_lowest: bool = False):
         """Extension: threshold sparsification plus the min-max "-W" edge weights in one device pass.
@@ -309,13 +343,13 @@ class GraphSparsifier:
             mask = torch.ones(self.num_edges, dtype=torch.uint8, device=scores.device)
             if scores.numel() < self.num_edges:
                 raise IndexError("boolean index did not match indexed array (duplicate edges)")
-            kept = self.num_edges
-        else:
-            mask, kept = self._threshold_mask(scores, int(self.num_edges * retention_ratio), keep_lowest)
-        ei, w, _ = compact_edges(self._ei_dev, mask, kept, scores=scores, with_weights=True, invert_weights=keep_lowest)
-        sparse_data = self.data.clone()
-        sparse_data.edge_index = ei.to(self.device)
-        return sparse_data, w.to(self.device), _to_host(mask.view(torch.bool))
+            ei, w, _ = compact_edges(self._ei_dev, mask, self.num_edges, scores=scores, with_weights=True, invert_weights=keep_lowest)
+            sparse_data = self.data.clone()
+            sparse_data.edge_index = ei.to(self.device)
+            return sparse_data, w.to(self.device), _to_host(mask.view(torch.bool))
+        take = self._take(int(self.num_edges * retention_ratio), keep_lowest, scores.numel())
+        sparse_data, w, mask = self._select_finish(scores, take, keep_lowest, True, with_weights=True)
+        return sparse_data, w.to(self.device), mask
 
     def sparsify_metric_backbone(self, metric: str, epsilon: float = 1e-9):
         """Global metric backbone: keep edge (u,v) iff its cost <= shortest-path cost + epsilon (reference core.py:251-279).

@@ -45,20 +45,21 @@ void count_launch();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// graph.cu: once per device, lets the default stream-ordered pool KEEP freed scratch across synchronisation points (the
-// default release threshold of 0 hands everything back to the driver at every sync, and the next call pays the mapping
-// of its scratch again: ~50 ms per call for the 134 MB weight table of the Adamic-Adar pass). gsp_trim_scratch releases it.
-void configure_scratch_pool();
+// graph.cu: the library's private stream-ordered pool on the current device (created on first use). It keeps a bounded
+// amount of freed scratch across synchronisation points (GSP_SCRATCH_KEEP_MB, default 1 GiB) and releases the rest to the
+// driver; gsp_trim_scratch releases all of it. nullptr: pool creation failed, use the device's default pool.
+cudaMemPool_t scratch_pool();
 
-// Stream-ordered scratch buffer (cudaMallocAsync pool): freed on the same stream when it goes out of scope.
+// Stream-ordered scratch buffer from that pool: freed on the same stream when it goes out of scope.
 template <typename T>
 struct Scratch {
     T* ptr = nullptr;
     cudaStream_t stream = nullptr;
     cudaError_t alloc(size_t count, cudaStream_t s) {
         stream = s;
-        configure_scratch_pool();
-        return cudaMallocAsync(reinterpret_cast<void**>(&ptr), (count ? count : 1) * sizeof(T), s);
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (cudaMemPool_t pool = scratch_pool()) return cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ptr), bytes, pool, s);
+        return cudaMallocAsync(reinterpret_cast<void**>(&ptr), bytes, s);
     }
     ~Scratch() {
         if (ptr) cudaFreeAsync(ptr, stream);

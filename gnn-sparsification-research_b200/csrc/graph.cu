@@ -13,6 +13,8 @@
 #include <atomic>
 #include <new>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace gsp {
@@ -393,17 +395,35 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
 
 int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream_t s) { return inclusive_sum(in, out, count, s); }
 
-void configure_scratch_pool() {
-    static std::atomic<uint64_t> configured{0};   // one bit per device
+// Private stream-ordered pool per device for the library's scratch. It keeps up to GSP_SCRATCH_KEEP_MB (default 1024)
+// of freed memory across synchronisation points — the hot small buffers: the 134 MB weight tables of the Adamic-Adar
+// pass, select state, work-item keys (with the default threshold of 0 every call paid their mapping again: ~50 ms) —
+// and hands everything above that back to the driver at the next synchronisation, so the multi-GB CG vectors of an
+// ApproxER call do not stay invisible to torch's allocator while the GNN trains. The process-wide default pool of the
+// device is left alone (other cudaMallocAsync users keep their own behaviour).
+cudaMemPool_t scratch_pool() {
+    static std::mutex mutex;
+    static cudaMemPool_t pools[64] = {};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-    if ((configured.load(std::memory_order_relaxed) >> dev) & 1ull) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mutex);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;      // Scratch falls back to the default pool with its default threshold
+        }
+        uint64_t keep = 1024ull << 20;
+        if (const char* env = getenv("GSP_SCRATCH_KEEP_MB")) keep = (uint64_t)strtoull(env, nullptr, 10) << 20;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[dev] = pool;
     }
-    configured.fetch_or(1ull << dev, std::memory_order_relaxed);
+    return pools[dev];
 }
 
 int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
@@ -429,10 +449,10 @@ GSP_API uint64_t gsp_launch_count(void) { return gsp::g_launches.load(std::memor
 GSP_API int gsp_trim_scratch(void) {
     int dev = 0;
     GSP_CUDA_TRY(cudaGetDevice(&dev));
-    cudaMemPool_t pool;
-    GSP_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    (void)dev;
+    cudaMemPool_t pool = scratch_pool();
     GSP_CUDA_TRY(cudaDeviceSynchronize());
-    GSP_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    if (pool) GSP_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
     return GSP_OK;
 }
 

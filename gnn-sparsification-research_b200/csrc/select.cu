@@ -30,6 +30,14 @@ struct SelectState {
     int64_t num_keep;
     int32_t keep_lowest;
     int32_t empty;        // num_keep == 0: keep nothing
+    // single-GPU fast path (gsp_select_mask / gsp_select_compact; a multi-GPU caller would have to all-reduce these too):
+    // the smallest / largest live key of the current pass. When they are equal the boundary bucket is ONE tie class
+    // (Jaccard's and feature-cosine's exact zeros hold ~half of all edges), the key is known and the remaining
+    // histogram passes exit at once; the smallest key of pass 0 is the best score (an extremum of the "-W" weights).
+    int32_t local_only;
+    int32_t resolved;
+    unsigned long long live_min, live_max;
+    unsigned long long best_key;
     int64_t block_ties[kMaxBlocks];
 };
 static_assert(sizeof(SelectState) <= 64 + 8 * kMaxBlocks, "state layout");
@@ -40,68 +48,129 @@ __device__ __forceinline__ uint64_t select_key(double s, int keep_lowest) {
     return keep_lowest ? k : ~k;
 }
 
-__global__ void begin_kernel(SelectState* st, int64_t num_keep, int keep_lowest) {
+__global__ void begin_kernel(SelectState* st, int64_t num_keep, int keep_lowest, int local_only) {
     st->prefix = 0;
     st->remaining = num_keep;
     st->num_keep = num_keep;
     st->keep_lowest = keep_lowest;
     st->empty = num_keep <= 0;
+    st->local_only = local_only;
+    st->resolved = 0;
+    st->live_min = ~0ull;
+    st->live_max = 0ull;
+    st->best_key = ~0ull;
 }
 
+// One live key into the block histogram. Intra-warp aggregation in two rounds: the lanes that share the digit of the
+// first live lane add once, then the same among the lanes that are left, the rest add on their own. Exponent-level
+// passes put a warp on a handful of bins (scores in [0, 1] span few binades; an exact-zero tie class is one bin) and
+// conflicting shared-memory atomics serialise inside the instruction; mantissa-level passes are spread and fall
+// through both rounds with one lane each.
+__device__ __forceinline__ void tally_digit(unsigned int* sh, bool live, unsigned int digit) {
+    unsigned left = __ballot_sync(0xffffffffu, live);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        if (left == 0) return;
+        const int leader = __ffs(left) - 1;
+        const unsigned int lead_digit = __shfl_sync(0xffffffffu, digit, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, live && digit == lead_digit) & left;
+        if ((threadIdx.x & 31) == leader) atomicAdd(&sh[lead_digit], (unsigned int)__popc(same));
+        left &= ~same;
+        if (digit == lead_digit) live = false;
+    }
+    if (live && ((left >> (threadIdx.x & 31)) & 1u)) atomicAdd(&sh[digit], 1u);
+}
+
+// kVec: 16-byte loads (scores 16-byte aligned), four per thread in flight.
+template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
 histogram_kernel(const double* __restrict__ scores, int64_t count, const uint8_t* __restrict__ exclude,
-                 const SelectState* __restrict__ st, int pass, unsigned long long* __restrict__ hist) {
+                 SelectState* __restrict__ st, int pass, unsigned long long* __restrict__ hist) {
+    if (st->resolved) return;   // the boundary key is known: nothing left to histogram
     __shared__ unsigned int sh[kBins];
     for (int i = threadIdx.x; i < kBins; i += kThreads) sh[i] = 0;
     __syncthreads();
     const int shift = pass_shift(pass), bits = pass_bits(pass);
     const int keep_lowest = st->keep_lowest;
+    const bool extrema = st->local_only != 0;
     const uint64_t prefix = st->prefix;
     const int hi_shift = shift + bits;  // bits above the current digit must match the prefix
     const unsigned int digit_mask = (1u << bits) - 1u;
-    constexpr int kUnroll = 4;   // four independent 8-byte loads in flight per thread (the pass is latency bound otherwise)
-    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll;
-    for (int64_t base = blockIdx.x * (int64_t)kThreads * kUnroll; base < count; base += stride) {
-        double v[kUnroll];
-        uint8_t ex[kUnroll];
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    constexpr int kUnroll = 4;
+    constexpr int kPer = kVec ? 2 : 1;   // scores per load
+    const int64_t stride = (int64_t)gridDim.x * kThreads * kUnroll * kPer;
+    for (int64_t base = blockIdx.x * (int64_t)kThreads * kUnroll * kPer; base < count; base += stride) {
+        double v[kUnroll][kPer];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t i = base + u * kThreads + threadIdx.x;
-            v[u] = i < count ? scores[i] : 0.0;
-            ex[u] = (exclude && i < count) ? exclude[i] : 0;
+            const int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * kPer;
+            if (kVec) {
+                double2 t = make_double2(0.0, 0.0);
+                if (i + 1 < count) t = *reinterpret_cast<const double2*>(scores + i);
+                else if (i < count) t.x = scores[i];
+                v[u][0] = t.x;
+                v[u][kPer - 1] = t.y;
+            } else {
+                v[u][0] = i < count ? scores[i] : 0.0;
+            }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t i = base + u * kThreads + threadIdx.x;
-            bool live = i < count && !ex[u];
-            unsigned int digit = 0;
-            if (live) {
-                uint64_t k = select_key(v[u], keep_lowest);
-                if (hi_shift < 64 && (k >> hi_shift) != (prefix >> hi_shift)) live = false;
-                digit = (unsigned int)(k >> shift) & digit_mask;
-            }
-            // heavy tie classes (e.g. Jaccard's zeros) put whole warps on one bin: one atomic for the warp
-            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-            if (live_mask == 0) continue;
-            const int leader = __ffs(live_mask) - 1;
-            const unsigned int lead_digit = __shfl_sync(0xffffffffu, digit, leader);
-            const unsigned same = __ballot_sync(0xffffffffu, live && digit == lead_digit);
-            if (same == live_mask) {
-                if ((threadIdx.x & 31) == leader) atomicAdd(&sh[lead_digit], (unsigned int)__popc(live_mask));
-            } else if (live) {
-                atomicAdd(&sh[digit], 1u);
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) {
+                const int64_t i = base + ((int64_t)u * kThreads + threadIdx.x) * kPer + e;
+                bool live = i < count && !(exclude && exclude[i]);
+                unsigned int digit = 0;
+                if (live) {
+                    const uint64_t k = select_key(v[u][e], keep_lowest);
+                    if (hi_shift < 64 && (k >> hi_shift) != (prefix >> hi_shift)) live = false;
+                    digit = (unsigned int)(k >> shift) & digit_mask;
+                    if (live && extrema) {
+                        kmin = k < kmin ? k : kmin;
+                        kmax = k > kmax ? k : kmax;
+                    }
+                }
+                tally_digit(sh, live, digit);
             }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (1 << bits); i += kThreads)
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    if (extrema) {
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+            kmin = a < kmin ? a : kmin;
+            kmax = b > kmax ? b : kmax;
+        }
+        if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+            atomicMin(&st->live_min, kmin);
+            atomicMax(&st->live_max, kmax);
+        }
+    }
 }
 
 // One warp: find the bucket holding the `remaining`-th smallest live key and descend into it.
 __global__ void pick_kernel(SelectState* st, const unsigned long long* __restrict__ hist, int pass) {
-    if (st->empty) return;
+    if (st->empty || st->resolved) return;
     const int lane = threadIdx.x;
+    if (st->local_only) {
+        const unsigned long long lo = st->live_min, hi = st->live_max;
+        __syncwarp();
+        if (lane == 0) {
+            if (pass == 0) st->best_key = lo;
+            st->live_min = ~0ull;          // reset for the next pass
+            st->live_max = 0ull;
+        }
+        if (lo == hi) {                    // every live key is the same: the boundary bucket is one tie class
+            if (lane == 0) {
+                st->prefix = lo;           // `remaining` already says how many of its members are kept
+                st->resolved = 1;
+            }
+            return;
+        }
+    }
     const int bits = pass_bits(pass), shift = pass_shift(pass);
     const int nbins = 1 << bits, per = nbins / 32;
     unsigned long long local = 0;
@@ -388,6 +457,189 @@ compact_scatter_kernel(const int64_t* __restrict__ ei, int64_t ld, int64_t count
     }
 }
 
+// ---- fused tail of the single-GPU select: tie counts, mask, compaction, "-W" weights in two passes --------------------
+// Replaces count_ties + write_mask + compact_count + compact_scatter (four kernels, two of which re-read the mask) when
+// the caller wants the kept edge list anyway (`GraphSparsifier.sparsify`): tally = per-block numbers of keys below the
+// boundary key and equal to it (8 B / score), emit = mask bytes + kept edge_index columns (+ weights) in one sweep
+// (8 B score + 16 B edge + 1 B mask + 16 B per kept column). Positions inside a 1024-score tile come from ONE block
+// scan of the packed pair (below, ties): the number of kept ties before a position is a function of the tie rank alone.
+struct FusedScratch {
+    long long block_below[kMaxBlocks];
+    long long block_ties[kMaxBlocks];
+};
+constexpr int kTile = 4 * kThreads;   // scores per block iteration, four consecutive ones per thread
+
+__device__ __forceinline__ void load4(const double* __restrict__ scores, int64_t i, int64_t hi, bool vec, double (&v)[4]) {
+    if (vec && i + 3 < hi) {
+        const double2 a = *reinterpret_cast<const double2*>(scores + i), b = *reinterpret_cast<const double2*>(scores + i + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i + j < hi ? scores[i + j] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fused_tally_kernel(const double* __restrict__ scores, int64_t count, const SelectState* __restrict__ st, FusedScratch* fs) {
+    __shared__ unsigned long long sh[2];
+    if (threadIdx.x < 2) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int keep_lowest = st->keep_lowest;
+    const uint64_t t = st->prefix;
+    const bool vec = (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
+    int64_t chunk = (count + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + kTile - 1) / kTile * kTile;
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+    unsigned long long nb = 0, nt = 0;
+    if (!st->empty) {
+        for (int64_t i0 = lo + 4 * (int64_t)threadIdx.x; i0 < hi; i0 += 2 * kTile) {   // two tiles in flight
+            double v[2][4];
+            load4(scores, i0, hi, vec, v[0]);
+            load4(scores, i0 + kTile, hi, vec, v[1]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t i = i0 + u * kTile + j;
+                    const uint64_t k = select_key(v[u][j], keep_lowest);
+                    nb += i < hi && k < t;
+                    nt += i < hi && k == t;
+                }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        nt += __shfl_xor_sync(0xffffffffu, nt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh[0], nb);
+        atomicAdd(&sh[1], nt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fs->block_below[blockIdx.x] = (long long)sh[0];
+        fs->block_ties[blockIdx.x] = (long long)sh[1];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fused_emit_kernel(const double* __restrict__ scores, int64_t count, const SelectState* __restrict__ st,
+                  const FusedScratch* __restrict__ fs, const int64_t* __restrict__ ei, int64_t ld, int invert,
+                  uint8_t* __restrict__ mask, int64_t* __restrict__ out_ei, int64_t out_ld, float* __restrict__ out_w,
+                  int64_t* __restrict__ num_kept) {
+    __shared__ long long red[3][kThreads / 32];
+    __shared__ unsigned int warp_tot[2][kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int keep_lowest = st->keep_lowest;
+    const bool empty = st->empty;
+    const uint64_t t = st->prefix;
+    const long long need = st->remaining;
+    // ties / keys below the boundary in earlier blocks, and all ties
+    long long below_before = 0, ties_before = 0, ties_total = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) {
+        const long long tb = fs->block_ties[b];
+        ties_total += tb;
+        if (b < (int)blockIdx.x) {
+            ties_before += tb;
+            below_before += fs->block_below[b];
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        below_before += __shfl_xor_sync(0xffffffffu, below_before, o);
+        ties_before += __shfl_xor_sync(0xffffffffu, ties_before, o);
+        ties_total += __shfl_xor_sync(0xffffffffu, ties_total, o);
+    }
+    if (lane == 0) { red[0][warp] = below_before; red[1][warp] = ties_before; red[2][warp] = ties_total; }
+    __syncthreads();
+    below_before = ties_before = ties_total = 0;
+    for (int w = 0; w < kThreads / 32; ++w) { below_before += red[0][w]; ties_before += red[1][w]; ties_total += red[2][w]; }
+    // window of tie ranks (position order) that are kept: the highest ones for top-k, the lowest ones for keep_lowest
+    const long long win_lo = keep_lowest ? 0 : max(ties_total - need, 0ll);
+    const long long win_hi = keep_lowest ? min(need, ties_total) : ties_total;
+    auto kept_ties_before = [&](long long rank) { return max(min(rank, win_hi) - win_lo, 0ll); };
+    double mn = 0.0, denom = 1.0;
+    if (out_w) {   // extrema of the kept scores: the boundary key and the best key (no pass over the kept set needed)
+        const double s_t = key_to_double(keep_lowest ? t : ~t), s_best = key_to_double(keep_lowest ? st->best_key : ~st->best_key);
+        mn = keep_lowest ? s_best : s_t;
+        const double mx = keep_lowest ? s_t : s_best;
+        denom = __dadd_rn(__dsub_rn(mx, mn), 1e-8);   // (mx - mn + 1e-8), roman_empire_gpu.py:251
+    }
+    const bool vec = (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
+    int64_t chunk = (count + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + kTile - 1) / kTile * kTile;
+    const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
+    long long tie_base = ties_before, kept_base = below_before + kept_ties_before(ties_before);
+    int buf = 0;
+    for (int64_t base = lo; base < hi; base += kTile, buf ^= 1) {
+        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        double v[4];
+        load4(scores, i0, hi, vec, v);
+        bool below[4], tie[4];
+        unsigned int nb = 0, nt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t k = select_key(v[j], keep_lowest);
+            const bool in = i0 + j < hi && !empty;
+            below[j] = in && k < t;
+            tie[j] = in && k == t;
+            nb += below[j];
+            nt += tie[j];
+        }
+        // block-exclusive scan of (below << 16 | ties): a tile holds 1024 scores, neither half overflows
+        unsigned int packed = (nb << 16) | nt, incl = packed;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_tot[buf][warp] = incl;
+        __syncthreads();
+        unsigned int before = incl - packed, tile_tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            const unsigned int wt = warp_tot[buf][w];
+            if (w < warp) before += wt;
+            tile_tot += wt;
+        }
+        long long rank = tie_base + (before & 0xffffu);                       // tie rank of this thread's first tie
+        long long pos = kept_base + (before >> 16) + (kept_ties_before(rank) - kept_ties_before(tie_base));
+        unsigned char m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bool keep = below[j];
+            if (tie[j]) {
+                keep = rank >= win_lo && rank < win_hi;
+                ++rank;
+            }
+            m[j] = keep ? 1 : 0;
+            if (keep) {
+                if (pos < out_ld) {
+                    out_ei[pos] = ei[i0 + j];
+                    out_ei[out_ld + pos] = ei[ld + i0 + j];
+                    if (out_w) {
+                        double w = __ddiv_rn(__dsub_rn(v[j], mn), denom);
+                        if (invert) w = __dsub_rn(1.0, w);
+                        out_w[pos] = (float)w;  // torch.tensor(norm, dtype=float32): round to nearest
+                    }
+                }
+                ++pos;
+            }
+        }
+        if (mask) {
+            if (i0 + 3 < hi && (reinterpret_cast<uintptr_t>(mask + i0) & 3) == 0) {
+                *reinterpret_cast<uchar4*>(mask + i0) = make_uchar4(m[0], m[1], m[2], m[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j < hi) mask[i0 + j] = m[j];
+            }
+        }
+        const long long tile_ties = tile_tot & 0xffffu;
+        kept_base += (tile_tot >> 16) + (kept_ties_before(tie_base + tile_ties) - kept_ties_before(tie_base));
+        tie_base += tile_ties;
+    }
+    if (num_kept && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *num_kept = kept_base;
+}
+
 int blocks_for(int64_t count) {
     int64_t b = (count + 4 * kThreads - 1) / (4 * kThreads);
     if (b < 1) b = 1;
@@ -405,10 +657,27 @@ static_assert(sizeof(SelectState) <= GSP_SELECT_STATE_BYTES, "GSP_SELECT_STATE_B
 GSP_API int gsp_select_begin(void* d_state, int64_t num_keep, int keep_lowest, void* stream) {
     GSP_REQUIRE(d_state != nullptr, "d_state is NULL");
     GSP_REQUIRE(num_keep >= 0, "num_keep must be >= 0");
-    begin_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state), num_keep, keep_lowest ? 1 : 0);
+    begin_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state), num_keep, keep_lowest ? 1 : 0, 0);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
+
+namespace gsp {
+namespace {
+// begin + the six histogram / pick rounds on ONE device: live-key extrema on, so a boundary bucket that is a single tie
+// class ends the rounds early
+int select_boundary_local(const double* d_scores, int64_t count, const uint8_t* d_exclude, int64_t num_keep, int keep_lowest,
+                          SelectState* state, uint64_t* hist, void* stream) {
+    begin_kernel<<<1, 1, 0, as_stream(stream)>>>(state, num_keep, keep_lowest ? 1 : 0, 1);
+    GSP_CHECK_LAUNCH();
+    for (int p = 0; p < kPasses; ++p) {
+        if (int rc = gsp_select_histogram(d_scores, count, d_exclude, state, p, hist, stream)) return rc;
+        if (int rc = gsp_select_pick(state, hist, p, stream)) return rc;
+    }
+    return GSP_OK;
+}
+}  // namespace
+}  // namespace gsp
 
 GSP_API int gsp_select_histogram(const double* d_scores, int64_t count, const uint8_t* d_exclude, const void* d_state,
                                  int pass, uint64_t* d_hist, void* stream) {
@@ -418,9 +687,13 @@ GSP_API int gsp_select_histogram(const double* d_scores, int64_t count, const ui
     cudaStream_t s = as_stream(stream);
     GSP_CUDA_TRY(cudaMemsetAsync(d_hist, 0, kBins * sizeof(uint64_t), s));
     if (count == 0) return GSP_OK;
-    histogram_kernel<<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(
-        d_scores, count, d_exclude, reinterpret_cast<const SelectState*>(d_state), pass,
-        reinterpret_cast<unsigned long long*>(d_hist));
+    SelectState* st = reinterpret_cast<SelectState*>(const_cast<void*>(d_state));
+    if ((reinterpret_cast<uintptr_t>(d_scores) & 15) == 0)
+        histogram_kernel<true><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, d_exclude, st, pass,
+                                                                                   reinterpret_cast<unsigned long long*>(d_hist));
+    else
+        histogram_kernel<false><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, d_exclude, st, pass,
+                                                                                    reinterpret_cast<unsigned long long*>(d_hist));
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
@@ -472,13 +745,38 @@ GSP_API int gsp_select_mask(const double* d_scores, int64_t count, int64_t num_k
     GSP_CUDA_TRY(hist.alloc(kBins, s));
     GSP_CUDA_TRY(ties.alloc(2, s));
     GSP_CUDA_TRY(cudaMemsetAsync(ties.ptr, 0, 2 * sizeof(int64_t), s));
-    if (int rc = gsp_select_begin(state.ptr, num_keep, keep_lowest, stream)) return rc;
-    for (int p = 0; p < kPasses; ++p) {
-        if (int rc = gsp_select_histogram(d_scores, count, d_exclude, state.ptr, p, hist.ptr, stream)) return rc;
-        if (int rc = gsp_select_pick(state.ptr, hist.ptr, p, stream)) return rc;
-    }
+    if (int rc = select_boundary_local(d_scores, count, d_exclude, num_keep, keep_lowest, reinterpret_cast<SelectState*>(state.ptr),
+                                       hist.ptr, stream)) return rc;
     if (int rc = gsp_select_count_ties(d_scores, count, d_exclude, state.ptr, ties.ptr, stream)) return rc;
     return gsp_select_write_mask(d_scores, count, d_exclude, state.ptr, ties.ptr + 1, ties.ptr, or_into, d_mask, stream);
+}
+
+GSP_API int gsp_select_compact(const double* d_scores, int64_t count, int64_t num_keep, int keep_lowest,
+                               const int64_t* d_edge_index, int64_t ld, uint8_t* d_mask, int64_t* d_out_edge_index,
+                               int64_t out_ld, float* d_out_weight, int invert_weights, int64_t* d_num_kept, void* stream) {
+    GSP_REQUIRE(count >= 0 && num_keep >= 0 && ld >= count && out_ld >= 0, "bad sizes");
+    cudaStream_t s = as_stream(stream);
+    if (count == 0) {
+        if (d_num_kept) GSP_CUDA_TRY(cudaMemsetAsync(d_num_kept, 0, sizeof(int64_t), s));
+        return GSP_OK;
+    }
+    GSP_REQUIRE(d_scores && d_edge_index, "NULL argument");
+    GSP_REQUIRE(out_ld == 0 || d_out_edge_index, "d_out_edge_index is NULL");
+    Scratch<char> state;
+    Scratch<uint64_t> hist;
+    Scratch<FusedScratch> fs;
+    GSP_CUDA_TRY(state.alloc(GSP_SELECT_STATE_BYTES, s));
+    GSP_CUDA_TRY(hist.alloc(kBins, s));
+    GSP_CUDA_TRY(fs.alloc(1, s));
+    SelectState* st = reinterpret_cast<SelectState*>(state.ptr);
+    if (int rc = select_boundary_local(d_scores, count, nullptr, num_keep, keep_lowest, st, hist.ptr, stream)) return rc;
+    const int blocks = blocks_for(count);
+    fused_tally_kernel<<<blocks, kThreads, 0, s>>>(d_scores, count, st, fs.ptr);
+    GSP_CHECK_LAUNCH();
+    fused_emit_kernel<<<blocks, kThreads, 0, s>>>(d_scores, count, st, fs.ptr, d_edge_index, ld, invert_weights, d_mask,
+                                                  d_out_edge_index, out_ld, d_out_weight, d_num_kept);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
 }
 
 GSP_API int gsp_degree_aware_guarantee(const int64_t* d_src, const double* d_scores, int64_t count, int64_t num_nodes,

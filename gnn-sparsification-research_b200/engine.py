@@ -231,6 +231,23 @@ class DeviceGraph:
         xhat._gsp_packed = use_packed
         return xhat
 
+    def normalize_rows(self, x_rows: torch.Tensor, out: torch.Tensor) -> bool:
+        """Normalise a block of feature rows into `out` (same shape): the row-sharded form of `normalize_features`
+        (rows are independent, so blocks normalised on different ranks concatenate to the full result). Returns whether
+        the packed layout was used; the caller tags the assembled tensor with `_gsp_packed`."""
+        if x_rows.dim() != 2 or out.shape != x_rows.shape or out.dtype != x_rows.dtype:
+            raise ValueError("x_rows and out must be [rows, d] tensors of the same shape and dtype")
+        x_rows = x_rows.contiguous()
+        dim = x_rows.size(1)
+        packed = x_rows.dtype == torch.float32 and dim in (32, 64, 96, 128)
+        if packed:
+            fn = self._lib.gsp_featcos_normalize_f32_packed
+        else:
+            fn = self._lib.gsp_featcos_normalize_f32 if x_rows.dtype == torch.float32 else self._lib.gsp_featcos_normalize_f64
+        with torch.cuda.device(self.device):
+            check(fn(x_rows.size(0), dim, ptr(x_rows), dim, ptr(out), out.stride(0), self._stream()))
+        return packed
+
     def feature_cosine(self, xhat: torch.Tensor, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         score = self._empty(e - b, torch.float64) if out is None else out
@@ -286,6 +303,29 @@ def select_mask_sharded(scores: torch.Tensor, num_keep: int, keep_lowest: bool, 
     from .sharding import LibgspSelectOps, distributed_select
 
     return distributed_select(LibgspSelectOps(scores, exclude, out, or_into), num_keep, keep_lowest, group)
+
+
+def select_compact(scores: torch.Tensor, num_keep: int, keep_lowest: bool, edge_index: torch.Tensor,
+                   mask: Optional[torch.Tensor] = None, with_weights: bool = False, invert_weights: bool = False,
+                   out: Optional[torch.Tensor] = None):
+    """Threshold selection + `edge_index[:, mask]` (+ min-max "-W" weights) in one library call (`gsp_select_compact`).
+
+    `scores` covers the first `scores.numel()` columns of `edge_index` (positional aliasing: canonical position p <->
+    column p); `mask` (uint8, >= scores.numel() entries, optional) receives the keep flags of those columns. Returns
+    (kept edge_index [2, capacity], weights or None, device int64[1] count); capacity = min(num_keep, n) columns."""
+    lib = _lib.load()
+    dev = scores.device
+    n = scores.numel()
+    ei = edge_index if edge_index.is_contiguous() else edge_index.contiguous()
+    cap = min(int(num_keep), n)
+    if out is None:
+        out = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    w = torch.empty(out.size(1), dtype=torch.float32, device=dev) if with_weights else None
+    count = torch.empty(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gsp_select_compact(ptr(scores), n, int(num_keep), int(bool(keep_lowest)), ptr(ei), ei.size(1), ptr(mask),
+                                     ptr(out), out.size(1), ptr(w), int(bool(invert_weights)), ptr(count), stream_ptr(dev)))
+    return out, w, count
 
 
 def degree_aware_guarantee(src: torch.Tensor, scores: torch.Tensor, num_nodes: int, min_per_node: int):

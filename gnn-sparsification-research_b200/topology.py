@@ -98,7 +98,14 @@ def topology_metrics_on_graph(g: DeviceGraph, dense_limit: int = 8192, with_conn
 
 
 def compute_topology_metrics(adj, dense_limit: int = 8192) -> Dict:
-    """reference metrics.py:445-520."""
+    """reference metrics.py:445-520. An asymmetric matrix (what sparsify_sampled / sparsify_degree_aware / a directed
+    top-k boundary leave behind) is read like the reference's `nx.from_scipy_sparse_array(adj)` reads it: an undirected
+    edge wherever either direction is stored (weight: the larger of the two entries)."""
+    import scipy.sparse as sp
+
+    adj = sp.csr_matrix(adj)
+    if (adj != adj.T).nnz:
+        adj = sp.csr_matrix(adj.maximum(adj.T))
     return topology_metrics_on_graph(graph_from_scipy(adj), dense_limit=dense_limit)
 
 
@@ -109,8 +116,9 @@ def compute_topology_preservation(original_adj, sparse_adj) -> Dict:
         "edge_retention": sparse["num_edges"] / orig["num_edges"] if orig["num_edges"] > 0 else 0.0,
         "clustering_preservation": (sparse["clustering_coefficient"] / orig["clustering_coefficient"]
                                     if orig["clustering_coefficient"] > 0 else 1.0),
+        # (NaN — a component beyond the dense eigen-solver's limit — propagates instead of reading as "0 preserved")
         "connectivity_preservation": (sparse["algebraic_connectivity"] / orig["algebraic_connectivity"]
-                                      if orig["algebraic_connectivity"] > 0 else 0.0),
+                                      if not orig["algebraic_connectivity"] <= 0 else 0.0),
         "component_change": sparse["num_connected_components"] - orig["num_connected_components"],
         "original_metrics": orig,
         "sparse_metrics": sparse,

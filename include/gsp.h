@@ -62,8 +62,9 @@ int gsp_version(void);
 const char* gsp_last_error(void);
 /* Number of CUDA kernels this library has launched in the process so far (monotonic; for benchmarks). */
 uint64_t gsp_launch_count(void);
-/* The library keeps its stream-ordered scratch (cudaMallocAsync default pool of the current device) across calls;
- * this hands the unused part back to the driver (synchronises the device). */
+/* The library allocates its scratch from a private stream-ordered pool per device that keeps at most GSP_SCRATCH_KEEP_MB
+ * (default 1024) of freed memory across synchronisation points; this hands all of it back to the driver (synchronises
+ * the device). */
 int gsp_trim_scratch(void);
 
 /* ---- graph ----------------------------------------------------------------------------------
@@ -212,7 +213,8 @@ int gsp_sssp_sources(const gsp_graph* g, const double* d_weights, const int32_t*
  * Contract (the reference run with a stable argsort): top-k keeps {s > t} plus the
  * HIGHEST-position members of {s == t}; keep_lowest keeps {s < t} plus the LOWEST-position members.
  * `state` is GSP_SELECT_STATE_BYTES of caller-owned device memory. Everything is stream-ordered; no
- * host synchronisation. gsp_select_mask runs the whole sequence for one GPU.
+ * host synchronisation. gsp_select_mask runs the whole sequence for one GPU (and, knowing that no other rank holds
+ * keys, stops the histogram rounds as soon as the boundary bucket turns out to be a single tie class).
  * num_keep must be in [0, number of non-excluded scores]. */
 #define GSP_SELECT_BINS 2048
 #define GSP_SELECT_PASSES 6
@@ -229,6 +231,16 @@ int gsp_select_write_mask(const double* d_scores, int64_t count, const uint8_t* 
                           void* stream);
 int gsp_select_mask(const double* d_scores, int64_t count, int64_t num_keep, int keep_lowest,
                     const uint8_t* d_exclude, int or_into, uint8_t* d_mask, void* stream);
+
+/* Single-GPU select + mask + compaction (+ "-W" weights) in one call — what `GraphSparsifier.sparsify` needs
+ * (reference core.py:232-245, roman_empire_gpu.py:248-256): the same boundary search as gsp_select_mask, then two
+ * passes instead of four (per-block counts; mask bytes + kept edge_index columns + weights in one sweep). The extrema
+ * of the kept scores are the boundary score and the best score, so the weights need no pass of their own. d_mask
+ * (uint8[count]) and d_out_weight (fp32[out_ld]) may be NULL; d_edge_index is int64 [2, count] with row stride ld;
+ * outputs as gsp_compact_edges. */
+int gsp_select_compact(const double* d_scores, int64_t count, int64_t num_keep, int keep_lowest,
+                       const int64_t* d_edge_index, int64_t ld, uint8_t* d_mask, int64_t* d_out_edge_index,
+                       int64_t out_ld, float* d_out_weight, int invert_weights, int64_t* d_num_kept, void* stream);
 
 /* Degree-aware guarantee phase — replaces reference core.py:421-435: for every source node
  * (d_src = edge_index[0], positional, any order) mark its top min(min_per_node, out-degree) edges by

@@ -32,6 +32,12 @@ def graphs():
     row = np.concatenate([a, b, loops])
     col = np.concatenate([b, a, loops])
     yield "blocks_with_loops", np.vstack([row, col]), 70
+    # a sparsified graph as sparsify_sampled / sparsify_degree_aware leave it: (u, v) kept without (v, u); the reference's
+    # nx.from_scipy_sparse_array takes either direction as the undirected edge (metrics.py:461-462)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rmat_300.npz"))
+    ei = g["edge_index"]
+    keep = (ei[0] * 31 + ei[1] * 17) % 5 != 0
+    yield "asymmetric_kept", ei[:, keep], int(g["num_nodes"])
 
 
 def adjacency(ei, n):

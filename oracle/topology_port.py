@@ -3,7 +3,8 @@
 the reference evaluates through NetworkX. Only tests/ may import this module. Pinned against the live reference (NetworkX
 3.6.1 in the build container) by tests/test_oracle_pin.py and against tests/golden/topology_metrics.json.
 
-Semantics restated (symmetric adjacency, as every caller passes):
+Semantics restated (an asymmetric matrix — a sampled / degree-aware sparsified graph — is read as the undirected graph
+with an edge wherever either direction is stored):
 * `nx.from_scipy_sparse_array(adj)`: one undirected edge per non-zero pair, a diagonal entry is a self loop;
   `number_of_edges` counts a loop once, `degree` counts it twice (metrics.py:461-465).
 * `nx.average_clustering`: per node `2 T(v) / (d(d-1))` over the neighbour set WITHOUT the node itself, 0 when d < 2,
@@ -21,6 +22,8 @@ from scipy.sparse.csgraph import connected_components
 
 def compute_topology_metrics(adj: sp.csr_matrix, with_connectivity: bool = True) -> dict:
     adj = sp.csr_matrix(adj)
+    if (adj != adj.T).nnz:      # nx.from_scipy_sparse_array builds an UNDIRECTED graph: either direction is the edge
+        adj = sp.csr_matrix(adj.maximum(adj.T))
     n = adj.shape[0]
     pattern = sp.csr_matrix((np.ones(adj.nnz), adj.indices, adj.indptr), shape=adj.shape)
     diag = pattern.diagonal()

@@ -1,0 +1,132 @@
+"""Real multi-rank run of the sharded engine (NCCL, one process per GPU; skipped with fewer than two devices).
+
+Every rank builds `GraphSparsifier(data, device, group=...)` — the sharded engine behind the reference API — and checks
+its slices / masks / kept edge lists against (1) the single-GPU engine on the same device, bit for bit, and (2) the C
+oracle. Covers the peer-store fused Jaccard + Adamic-Adar pass, the row-sharded feature normalisation, the distributed
+radix select, the sharded "-W" weights (min / max all-reduce), and the replicated degree-aware / sampled variants
+(reference src/sparsification/core.py:193-461, scripts/nb05_roman_empire/roman_empire_gpu.py:248-256)."""
+import os
+import socket
+import traceback
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _hub_graph(n, hubs, seed):
+    """A few nodes adjacent to (almost) everything + a sparse random remainder: multi-tile hub rows, long streamed rows."""
+    rng = np.random.default_rng(seed)
+    lo, hi = [], []
+    for h in range(hubs):
+        others = np.setdiff1d(rng.choice(n, size=int(n * 0.7), replace=False), [h])
+        lo.append(np.minimum(h, others)); hi.append(np.maximum(h, others))
+    a, b = rng.integers(0, n, size=(2, 6 * n))
+    keep = a != b
+    lo.append(np.minimum(a, b)[keep]); hi.append(np.maximum(a, b)[keep])
+    keys = np.unique(np.concatenate(lo).astype(np.int64) * n + np.concatenate(hi))
+    l, h = keys // n, keys % n
+    row, col = np.concatenate([l, h]), np.concatenate([h, l])
+    order = np.lexsort((col, row))
+    return np.vstack([row[order], col[order]])
+
+
+def _worker(rank, world, port, fail):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch.distributed as dist
+
+        import gsr_b200
+        from gsr_b200.sharded_sparsifier import ShardedGraphSparsifier, sharded_to_device
+        from gsr_b200.synthetic import features, rmat_graph
+        from oracle import c_oracle as co
+
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        group = dist.group.WORLD
+        cases = {"hub": (9000, _hub_graph(9000, 4, 7)), "rmat": (20000, rmat_graph(20000, 400000, 15, seed=3))}
+        for name, (n, ei) in cases.items():
+            x = features(n, 64, 11)
+            host = gsr_b200.Data(edge_index=torch.from_numpy(ei).pin_memory(), x=torch.from_numpy(x).pin_memory(), num_nodes=n)
+            data = sharded_to_device(host, dev, group)                 # 1/N upload + NVLink all-gather
+            assert torch.equal(data.edge_index.cpu(), host.edge_index) and torch.equal(data.x.cpu(), host.x), name
+            single = gsr_b200.GraphSparsifier(data, str(dev))
+            sp = gsr_b200.GraphSparsifier(data, str(dev), group=group)
+            assert isinstance(sp, ShardedGraphSparsifier) and sp.sharded
+            sp.approx_er_options.update(k=8)
+            single.approx_er_options.update(k=8)
+            lo, hi = sp.local_range
+            e = ei.shape[1]
+            assert (lo, hi) == (rank * ((e + world - 1) // world), min(e, (rank + 1) * ((e + world - 1) // world)))
+            sp.prefetch_scores(["jaccard", "adamic_adar", "feature_cosine"])    # fused pass, peer stores
+            csr = co.csr_from_edge_index(ei, n)
+            oracle = {"jaccard": co.calculate_jaccard_scores(csr), "adamic_adar": co.calculate_adamic_adar_scores(csr),
+                      "feature_cosine": co.calculate_feature_cosine_scores(csr, x)}
+            for m in ("jaccard", "adamic_adar", "feature_cosine", "degree", "approx_er"):
+                mine = sp.compute_scores(m)
+                ref = single.compute_scores(m)
+                assert mine.shape == (hi - lo,), (name, m)
+                if m == "approx_er":      # column-sharded sums are all-reduced: a different association of the k partial sums
+                    np.testing.assert_allclose(mine, ref[lo:hi], rtol=1e-9, err_msg=f"{name} {m}")
+                else:
+                    assert mine.tobytes() == ref[lo:hi].tobytes(), (name, m)
+                if m in oracle:
+                    assert mine.tobytes() == oracle[m][lo:hi].tobytes(), (name, m, "oracle")
+            for m in ("jaccard", "adamic_adar", "feature_cosine"):
+                for r, low in ((0.5, False), (0.3, True), (0.9, False)):
+                    d1, m1 = sp.sparsify(m, r, return_mask=True, keep_lowest=low)
+                    d0, m0 = single.sparsify(m, r, return_mask=True, keep_lowest=low)
+                    assert torch.equal(m1, m0[lo:hi]), (name, m, r, low)
+                    assert torch.equal(d1.edge_index, d0.edge_index), (name, m, r, low)
+                    want = co.threshold_mask(oracle[m], e, r, keep_lowest=low)
+                    assert np.array_equal(m1.numpy(), want[lo:hi]), (name, m, r, low, "oracle")
+                d1, w1, m1 = sp.sparsify_with_weights(m, 0.4, keep_lowest=(m == "jaccard"))
+                d0, w0, m0 = single.sparsify_with_weights(m, 0.4, keep_lowest=(m == "jaccard"))
+                assert torch.equal(d1.edge_index, d0.edge_index) and torch.equal(m1, m0[lo:hi]), (name, m, "-W")
+                assert torch.equal(w1, w0), (name, m, "-W weights")
+            for m in ("jaccard", "adamic_adar"):
+                d1, m1 = sp.sparsify_degree_aware(m, 0.35, return_mask=True)
+                d0, m0 = single.sparsify_degree_aware(m, 0.35, return_mask=True)
+                assert torch.equal(d1.edge_index, d0.edge_index) and torch.equal(m1, m0[lo:hi]), (name, m, "degree-aware")
+            if name == "hub":
+                d1, m1 = sp.sparsify_sampled("jaccard", 0.5, seed=3, return_mask=True)
+                d0, m0 = single.sparsify_sampled("jaccard", 0.5, seed=3, return_mask=True)
+                assert torch.equal(d1.edge_index, d0.edge_index) and torch.equal(m1, m0[lo:hi]), (name, "sampled")
+            # full vectors on demand
+            full = gsr_b200.GraphSparsifier(data, str(dev), group=group, gather_outputs=True)
+            assert full.compute_scores("jaccard").tobytes() == oracle["jaccard"].tobytes(), name
+            _, mf = full.sparsify("jaccard", 0.5, return_mask=True)
+            assert np.array_equal(mf.numpy(), co.threshold_mask(oracle["jaccard"], e, 0.5)), name
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        fail.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_sharded_sparsifier_matches_single_gpu_and_oracle_world2():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    fail = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, fail)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    errors = []
+    while not fail.empty():
+        errors.append(fail.get())
+    assert not errors, "\n".join(f"rank {r}:\n{tb}" for r, tb in errors)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]

@@ -205,7 +205,7 @@ def test_topology_port_matches_goldens_and_live_reference():
                 assert abs(got[k] - want[k]) <= 1e-12 * max(1.0, abs(want[k])), (name, k)
             assert abs(got["algebraic_connectivity"] - want["algebraic_connectivity"]) <= 1e-6 * max(1.0, want["algebraic_connectivity"]), name
         seen += 1
-    assert seen == len(gold) == 9
+    assert seen == len(gold) == 10
 
 
 def test_geodesic_port_matches_goldens():
