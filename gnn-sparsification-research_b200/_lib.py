@@ -43,6 +43,7 @@ PROTOTYPES = {
     "gsp_last_error": (C.c_char_p, []),
     "gsp_launch_count": (C.c_uint64, []),
     "gsp_trim_scratch": (_INT, []),
+    "gsp_set_allocator": (_INT, [_P, _P]),
     "gsp_graph_create": (_INT, [_I64, _I64, _P, _P, _P, _P, C.POINTER(_P)]),
     "gsp_graph_destroy": (None, [_P]),
     "gsp_graph_get_info": (_INT, [_P, C.POINTER(GraphInfo)]),
@@ -107,7 +108,38 @@ def load():
             fn.restype = restype
             fn.argtypes = argtypes
         _lib = lib
+        _install_torch_allocator(lib)
     return _lib
+
+
+_ALLOC_CB = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+_FREE_CB = C.CFUNCTYPE(None, C.c_void_p)
+_allocator_callbacks = None      # keeps the ctypes thunks alive for the life of the process
+
+
+def _install_torch_allocator(lib) -> None:
+    """Hand torch's caching allocator to libgsp (include/gsp.h, gsp_set_allocator): graph arrays and scratch then come out
+    of — and go back to — the pool torch manages, so nothing the library frees stays invisible to the training that
+    follows, and building a graph per call recycles blocks instead of paying cudaMalloc / cudaFree of gigabytes.
+    GSP_ALLOCATOR=cuda keeps the library's own cudaMalloc + private scratch pool."""
+    global _allocator_callbacks
+    if os.environ.get("GSP_ALLOCATOR", "torch") != "torch" or not torch.cuda.is_available():
+        return
+
+    def alloc(nbytes, device, stream):
+        try:
+            return torch.cuda.caching_allocator_alloc(int(nbytes), int(device), int(stream or 0))
+        except Exception:
+            return None
+
+    def free(ptr):
+        try:
+            torch.cuda.caching_allocator_delete(ptr)
+        except Exception:
+            pass
+
+    _allocator_callbacks = (_ALLOC_CB(alloc), _FREE_CB(free))
+    lib.gsp_set_allocator(C.cast(_allocator_callbacks[0], C.c_void_p), C.cast(_allocator_callbacks[1], C.c_void_p))
 
 
 def require_cuda() -> None:

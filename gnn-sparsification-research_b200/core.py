@@ -38,6 +38,16 @@ def _to_host(t: torch.Tensor) -> torch.Tensor:
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_COPY_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    """One device-to-host copy stream per device for the whole process (read-backs overlap the kernels of the compute
+    stream and, the link being full duplex, the uploads still in flight)."""
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    if index not in _COPY_STREAMS:
+        _COPY_STREAMS[index] = torch.cuda.Stream(torch.device("cuda", index))
+    return _COPY_STREAMS[index]
 
 
 def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
@@ -81,6 +91,7 @@ class GraphSparsifier:
         self._side_pending = False
         self._ei_dev: Optional[torch.Tensor] = None
         self._dev_scores: Dict[str, torch.Tensor] = {}
+        self._host_pending: Dict[str, Tuple[torch.Tensor, "torch.cuda.Event"]] = {}   # read-backs in flight (prefetch_scores)
         self._xhat: Optional[torch.Tensor] = None
         # extensions (not in the reference signature): ApproxER knobs, AA weight source
         self.approx_er_options = dict(epsilon=0.3, seed=42, max_cg_iters=500, cg_tol=1e-6, k=None, projection=None)
@@ -120,6 +131,8 @@ class GraphSparsifier:
                 self._side.wait_event(ready)
                 with torch.cuda.stream(self._side):
                     self._graph = DeviceGraph(self._ei_dev, self.num_nodes)
+                    self._graph_ready = torch.cuda.Event()
+                    self._graph_ready.record(self._side)
                 self._ei_dev.record_stream(self._side)
                 self._side_pending = True
             else:
@@ -127,16 +140,26 @@ class GraphSparsifier:
         return self._graph
 
     def _join_side(self) -> None:
-        """Work queued on the side stream (graph build, neighbourhood scoring started by `prefetch_scores`) becomes a
-        dependency of the caller's stream. Every access to the graph or to cached device scores goes through here."""
+        """ALL work queued on the side stream (graph build, neighbourhood scoring started by `prefetch_scores`) becomes a
+        dependency of the caller's stream. Every access to cached device scores goes through here."""
         if self._side_pending:
             torch.cuda.current_stream(self._side.device).wait_stream(self._side)
             self._side_pending = False
+            self._graph_ready = None
+
+    def _join_graph(self) -> None:
+        """Only the graph build becomes a dependency of the caller's stream: feature-cosine scoring (which needs the
+        graph and the features, not the neighbourhood scores) then runs beside the neighbourhood pass still on the side
+        stream instead of behind it."""
+        ready = getattr(self, "_graph_ready", None)
+        if ready is not None:
+            torch.cuda.current_stream(self._side.device).wait_event(ready)
+            self._graph_ready = None
 
     @property
     def graph(self) -> DeviceGraph:
         self._build_graph()
-        self._join_side()
+        self._join_graph()
         return self._graph
 
     @property
@@ -213,12 +236,13 @@ class GraphSparsifier:
         self._dev_scores[key] = t
         return t
 
-    def prefetch_scores(self, metrics) -> None:
+    def prefetch_scores(self, metrics, to_host: bool = False) -> None:
         """Extension: announce the metrics a caller is about to use (the reference's drivers loop over a fixed method list,
         scripts/nb05_roman_empire/roman_empire_gpu.py:81-102, src/experiments/ablation.py:220-270). Jaccard and Adamic-Adar
         requested together come from ONE streaming pass over the neighbour lists (`gsp_jaccard_adamic_adar`): the hit
         ballots of the ordered Adamic-Adar sum also give the intersection count. Results are bit-identical to separate
-        `compute_scores` calls; everything else is computed as usual and cached on the device."""
+        `compute_scores` calls; everything else is computed as usual and cached on the device. `to_host=True` also starts the
+        read-back of every announced vector as soon as its kernel is queued (see `_start_host_copies`)."""
         keys = [self._normalize_metric_name(m) for m in metrics]
         pending = [k for k in keys if k not in self._dev_scores and k not in self._score_cache]
         if "jaccard" in pending and "adamic_adar" in pending:
@@ -233,8 +257,35 @@ class GraphSparsifier:
             else:
                 jac, aa = g.jaccard_adamic_adar(self._aa_node_weights())
             self._dev_scores["jaccard"], self._dev_scores["adamic_adar"] = jac, aa
-        for k in keys:
-            self._device_scores(k)
+        fused_keys = [k for k in ("jaccard", "adamic_adar") if k in keys and k in self._dev_scores and self._side_pending]
+        for k in keys:      # everything else first: it runs (and is read back) beside the neighbourhood pass of the side stream
+            if k not in fused_keys:
+                self._device_scores(k)
+                if to_host:
+                    self._start_host_copies([k])
+        if to_host:
+            self._start_host_copies(fused_keys)
+
+    def _start_host_copies(self, keys) -> None:
+        """Queue the device-to-host copy of the fp64 vectors the reference API returns on the host (page-locked buffers,
+        a copy stream that waits only for the producing stream): `compute_scores` then waits for ITS vector instead of
+        running each 2 GB read-back after the previous kernel, one blocking copy at a time."""
+        for key in keys:
+            if key in self._score_cache or key in self._host_pending:
+                continue
+            t = self._dev_scores[key]
+            cs = _copy_stream(t.device)
+            producer = self._side if (self._side_pending and self._side is not None) else torch.cuda.current_stream(t.device)
+            ready = torch.cuda.Event()
+            ready.record(producer)
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            cs.wait_event(ready)
+            with torch.cuda.stream(cs):
+                host.copy_(t, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(cs)
+            t.record_stream(cs)
+            self._host_pending[key] = (host, done)
 
     def _aa_node_weights(self) -> Optional[torch.Tensor]:
         """Adamic-Adar node weights 1/sqrt(max(log(deg+1),1e-10)) (reference metrics.py:104-108).
@@ -259,7 +310,12 @@ class GraphSparsifier:
         """Edge scores as float64 ndarray in canonical CSR order (reference core.py:140-191)."""
         key = self._normalize_metric_name(metric)
         if key not in self._score_cache:
-            self._score_cache[key] = _to_host(self._device_scores(key)).numpy()
+            if key in self._host_pending:               # read-back started by prefetch_scores(to_host=True)
+                host, done = self._host_pending.pop(key)
+                done.synchronize()
+                self._score_cache[key] = host.numpy()
+            else:
+                self._score_cache[key] = _to_host(self._device_scores(key)).numpy()
         return self._score_cache[key]
 
     # ------------------------------------------------------------------------------ selection

@@ -485,15 +485,15 @@ int ensure_segments(Graph* g, cudaStream_t s) {
     Scratch<int64_t> counts;
     GSP_CUDA_TRY(counts.alloc(g->n, s));
     int64_t* incl = nullptr;
-    GSP_CUDA_TRY(cudaMalloc(&incl, (size_t)g->n * sizeof(int64_t)));
+    GSP_CUDA_TRY(device_alloc(&incl, (size_t)g->n * sizeof(int64_t), s));
     seg_count_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, counts.ptr);
     GSP_CHECK_LAUNCH();
-    if (int rc = inclusive_sum_i64(counts.ptr, incl, g->n, s)) { cudaFree(incl); return rc; }
+    if (int rc = inclusive_sum_i64(counts.ptr, incl, g->n, s)) { device_free(incl); return rc; }
     int64_t total = 0;
     GSP_CUDA_TRY(cudaMemcpyAsync(&total, incl + (g->n - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     GSP_CUDA_TRY(cudaStreamSynchronize(s));
     SegItem* items = nullptr;
-    GSP_CUDA_TRY(cudaMalloc(&items, (size_t)total * sizeof(SegItem)));
+    GSP_CUDA_TRY(device_alloc(&items, (size_t)total * sizeof(SegItem), s));
     seg_fill_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, incl, items);
     GSP_CHECK_LAUNCH();
     GSP_CUDA_TRY(cudaStreamSynchronize(s));
@@ -507,10 +507,10 @@ int ensure_und_id(Graph* g, void* stream) {
     std::lock_guard<std::mutex> lock(g_und_mutex);
     if (g->und_id || g->nnz == 0) return GSP_OK;
     int32_t* buf = nullptr;
-    GSP_CUDA_TRY(cudaMalloc(&buf, (size_t)g->nnz * sizeof(int32_t)));
+    GSP_CUDA_TRY(device_alloc(&buf, (size_t)g->nnz * sizeof(int32_t), as_stream(stream)));
     int rc = gsp_graph_undirected_ids(reinterpret_cast<gsp_graph*>(g), buf, stream);
     if (rc) {
-        cudaFree(buf);
+        device_free(buf);
         return rc;
     }
     g->und_id = buf;

@@ -50,7 +50,24 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // driver; gsp_trim_scratch releases all of it. nullptr: pool creation failed, use the device's default pool.
 cudaMemPool_t scratch_pool();
 
-// Stream-ordered scratch buffer from that pool: freed on the same stream when it goes out of scope.
+// Device memory of the library (graph arrays, lazily built side structures, scratch). A host may plug its own allocator
+// in (gsp_set_allocator: the Python layer hands over torch's caching allocator), so that nothing the library holds is
+// invisible to the host framework and repeated graph builds reuse blocks instead of paying cudaMalloc / cudaFree of
+// gigabytes every time; without one: cudaMalloc / cudaFree for persistent arrays, the private pool for scratch.
+void* device_alloc_bytes(size_t bytes, cudaStream_t s);   // nullptr on failure
+void device_free_bytes(void* p);
+bool custom_allocator();
+template <typename T>
+inline cudaError_t device_alloc(T** out, size_t bytes, cudaStream_t s) {
+    *out = static_cast<T*>(device_alloc_bytes(bytes, s));
+    return *out ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+inline cudaError_t device_free(void* p) {
+    device_free_bytes(p);
+    return cudaSuccess;
+}
+
+// Stream-ordered scratch buffer (plugged allocator, else the private pool): freed on the same stream when it goes out of scope.
 template <typename T>
 struct Scratch {
     T* ptr = nullptr;
@@ -58,11 +75,19 @@ struct Scratch {
     cudaError_t alloc(size_t count, cudaStream_t s) {
         stream = s;
         const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (custom_allocator()) {
+            hosted = true;
+            ptr = static_cast<T*>(device_alloc_bytes(bytes, s));
+            return ptr ? cudaSuccess : cudaErrorMemoryAllocation;
+        }
         if (cudaMemPool_t pool = scratch_pool()) return cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ptr), bytes, pool, s);
         return cudaMallocAsync(reinterpret_cast<void**>(&ptr), bytes, s);
     }
+    bool hosted = false;   // from the plugged allocator (its free is ordered on the allocation stream, like cudaFreeAsync)
     ~Scratch() {
-        if (ptr) cudaFreeAsync(ptr, stream);
+        if (!ptr) return;
+        if (hosted) device_free_bytes(ptr);
+        else cudaFreeAsync(ptr, stream);
     }
     Scratch() = default;
     Scratch(const Scratch&) = delete;
@@ -98,6 +123,11 @@ struct Graph {
     int64_t num_owner_items = 0; // medium-class items (first in the array)
     int64_t num_hub_items = 0;   // hub-class items (after them)
     bool owner_items_ready = false;
+    // the work items whose owner lies in [owned_lo, owned_hi) (owner-sharded scoring: a rank would otherwise claim and
+    // skip the items of all other ranks, 7/8 of ~6 x 10^5 claims on 8 GPUs); rebuilt when the range changes
+    void* owned_items = nullptr;
+    int64_t num_owned_items = 0, num_owned_hub_items = 0;
+    int64_t owned_lo = -1, owned_hi = -1;
 };
 
 // graph.cu: CUB inclusive scan wrapper shared by the lazily built side structures

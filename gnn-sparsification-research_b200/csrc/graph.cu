@@ -232,17 +232,25 @@ int bits_for(int64_t n) {
 
 void free_graph(Graph* g) {
     if (!g) return;
-    cudaFree(g->indptr);
-    cudaFree(g->indices);
-    cudaFree(g->rows);
-    cudaFree(g->data);
-    cudaFree(g->tptr);
-    cudaFree(g->tidx);
-    cudaFree(g->und_id);
-    cudaFree(g->rev_off);
-    cudaFree(g->owner_items);
-    cudaFree(g->seg_items);
-    cudaFree(g->seg_incl);
+    if (custom_allocator()) {   // a freed block may be handed out again at once: no stream may still be reading the graph
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != g->device) cudaSetDevice(g->device);
+        cudaDeviceSynchronize();
+        if (cur != g->device) cudaSetDevice(cur);
+    }
+    device_free(g->indptr);
+    device_free(g->indices);
+    device_free(g->rows);
+    device_free(g->data);
+    device_free(g->tptr);
+    device_free(g->tidx);
+    device_free(g->und_id);
+    device_free(g->rev_off);
+    device_free(g->owner_items);
+    device_free(g->owned_items);
+    device_free(g->seg_items);
+    device_free(g->seg_incl);
     delete g;
 }
 
@@ -298,12 +306,12 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
     g->input_canonical = !hf.not_canonical && !hf.has_zero;
     const bool keep_values = d_val && hf.non_unit;
 
-    GSP_CUDA_TRY(cudaMalloc(&g->indptr, (size_t)(n + 1) * sizeof(int64_t)));
+    GSP_CUDA_TRY(device_alloc(&g->indptr, (size_t)(n + 1) * sizeof(int64_t), s));
     if (g->input_canonical) {
         g->nnz = E;
-        GSP_CUDA_TRY(cudaMalloc(&g->indices, (size_t)(E ? E : 1) * sizeof(int32_t)));
-        GSP_CUDA_TRY(cudaMalloc(&g->rows, (size_t)(E ? E : 1) * sizeof(int32_t)));
-        if (keep_values) GSP_CUDA_TRY(cudaMalloc(&g->data, (size_t)(E ? E : 1) * sizeof(double)));
+        GSP_CUDA_TRY(device_alloc(&g->indices, (size_t)(E ? E : 1) * sizeof(int32_t), s));
+        GSP_CUDA_TRY(device_alloc(&g->rows, (size_t)(E ? E : 1) * sizeof(int32_t), s));
+        if (keep_values) GSP_CUDA_TRY(device_alloc(&g->data, (size_t)(E ? E : 1) * sizeof(double), s));
         if (E > 0) {
             narrow_kernel<<<grid, threads, 0, s>>>(E, d_row, d_col, d_val, g->rows, g->indices, g->data);
             GSP_CHECK_LAUNCH();
@@ -330,9 +338,9 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
         GSP_CUDA_TRY(cudaMemcpyAsync(&nnz, pos.ptr + (E - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         GSP_CUDA_TRY(cudaStreamSynchronize(s));
         g->nnz = nnz;
-        GSP_CUDA_TRY(cudaMalloc(&g->indices, (size_t)nnz * sizeof(int32_t)));
-        GSP_CUDA_TRY(cudaMalloc(&g->rows, (size_t)nnz * sizeof(int32_t)));
-        GSP_CUDA_TRY(cudaMalloc(&g->data, (size_t)nnz * sizeof(double)));
+        GSP_CUDA_TRY(device_alloc(&g->indices, (size_t)nnz * sizeof(int32_t), s));
+        GSP_CUDA_TRY(device_alloc(&g->rows, (size_t)nnz * sizeof(int32_t), s));
+        GSP_CUDA_TRY(device_alloc(&g->data, (size_t)nnz * sizeof(double), s));
         merge_runs_kernel<<<grid, threads, 0, s>>>(E, keys_sorted.ptr, pos.ptr, d_val ? val_sorted.ptr : nullptr, shift,
                                                    g->rows, g->indices, g->data);
         GSP_CHECK_LAUNCH();
@@ -346,7 +354,7 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
     degree_stats_kernel<<<grid_for(n, threads), threads, 0, s>>>(n, g->indptr, stats.ptr);
     GSP_CHECK_LAUNCH();
     if (g->nnz > 0) {
-        GSP_CUDA_TRY(cudaMalloc(&g->rev_off, (size_t)g->nnz * sizeof(int32_t)));
+        GSP_CUDA_TRY(device_alloc(&g->rev_off, (size_t)g->nnz * sizeof(int32_t), s));
         edge_stats_kernel<<<grid_for(g->nnz, threads), threads, 0, s>>>(g->nnz, g->indptr, g->indices, g->rows, g->data,
                                                                         stats.ptr, g->rev_off);
         GSP_CHECK_LAUNCH();
@@ -364,7 +372,7 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
     g->symmetric = !hs.asymmetric;
     g->unit_weights = !(g->data && hs.non_unit);
     if (g->data && g->unit_weights) {  // multiplicities all 1: no need to keep 8*nnz bytes around
-        GSP_CUDA_TRY(cudaFree(g->data));
+        GSP_CUDA_TRY(device_free(g->data));
         g->data = nullptr;
     }
 
@@ -376,8 +384,8 @@ int build_graph(Graph* g, int64_t n, int64_t E, const int64_t* d_row, const int6
         GSP_CUDA_TRY(keys.alloc(nnz, s));
         GSP_CUDA_TRY(keys_sorted.alloc(nnz, s));
         GSP_CUDA_TRY(trow.alloc(nnz, s));
-        GSP_CUDA_TRY(cudaMalloc(&g->tptr, (size_t)(n + 1) * sizeof(int64_t)));
-        GSP_CUDA_TRY(cudaMalloc(&g->tidx, (size_t)nnz * sizeof(int32_t)));
+        GSP_CUDA_TRY(device_alloc(&g->tptr, (size_t)(n + 1) * sizeof(int64_t), s));
+        GSP_CUDA_TRY(device_alloc(&g->tidx, (size_t)nnz * sizeof(int32_t), s));
         pack_keys32_kernel<<<grid_for(nnz, threads), threads, 0, s>>>(nnz, g->indices, g->rows, shift, keys.ptr);
         GSP_CHECK_LAUNCH();
         int rc = sort_keys(keys.ptr, keys_sorted.ptr, nullptr, nullptr, nnz, 2 * shift, s);
@@ -426,6 +434,36 @@ cudaMemPool_t scratch_pool() {
     return pools[dev];
 }
 
+namespace {
+gsp_alloc_fn g_alloc_fn = nullptr;
+gsp_free_fn g_free_fn = nullptr;
+}  // namespace
+
+bool custom_allocator() { return g_alloc_fn != nullptr; }
+
+void* device_alloc_bytes(size_t bytes, cudaStream_t s) {
+    if (bytes == 0) bytes = 1;
+    if (g_alloc_fn) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        void* p = g_alloc_fn(bytes, dev, reinterpret_cast<void*>(s));
+        if (!p) set_error("the host allocator could not provide %zu bytes", bytes);
+        return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void device_free_bytes(void* p) {
+    if (!p) return;
+    if (g_free_fn) g_free_fn(p);
+    else cudaFree(p);
+}
+
 int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
                        cudaStream_t s) {
     size_t tmp_bytes = 0;
@@ -445,6 +483,13 @@ GSP_API int gsp_version(void) { return GSP_VERSION; }
 GSP_API const char* gsp_last_error(void) { return gsp::g_error; }
 
 GSP_API uint64_t gsp_launch_count(void) { return gsp::g_launches.load(std::memory_order_relaxed); }
+
+GSP_API int gsp_set_allocator(gsp_alloc_fn alloc_fn, gsp_free_fn free_fn) {
+    GSP_REQUIRE((alloc_fn == nullptr) == (free_fn == nullptr), "give both functions or neither");
+    g_alloc_fn = alloc_fn;
+    g_free_fn = free_fn;
+    return GSP_OK;
+}
 
 GSP_API int gsp_trim_scratch(void) {
     int dev = 0;

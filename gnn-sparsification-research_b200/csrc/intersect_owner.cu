@@ -664,13 +664,13 @@ int ensure_items(Graph* g, cudaStream_t s) {
     GSP_CUDA_TRY(cudaStreamSynchronize(s));
     if (totals[0] + totals[1] > 0) {
         OwnerItem* items = nullptr;   // medium items first, hub items after them
-        GSP_CUDA_TRY(cudaMalloc(&items, (size_t)(totals[0] + totals[1]) * sizeof(OwnerItem)));
+        GSP_CUDA_TRY(device_alloc(&items, (size_t)(totals[0] + totals[1]) * sizeof(OwnerItem), s));
         fill_items_kernel<<<grid_for(g->n, 256), 256, 0, s>>>(g->n, g->indptr, im.ptr, ih.ptr, items, items + totals[0]);
         GSP_CHECK_LAUNCH();
         const char* order = getenv("GSP_ITEM_ORDER");   // "owner" keeps the owner-major order (for A/B measurements)
         if (!(order && order[0] == 'o')) {
-            if (int rc = sort_items_by_window(items, totals[0], g, s)) { cudaFree(items); return rc; }
-            if (int rc = sort_items_by_window(items + totals[0], totals[1], g, s)) { cudaFree(items); return rc; }
+            if (int rc = sort_items_by_window(items, totals[0], g, s)) { device_free(items); return rc; }
+            if (int rc = sort_items_by_window(items + totals[0], totals[1], g, s)) { device_free(items); return rc; }
         }
         GSP_CUDA_TRY(cudaStreamSynchronize(s));
         g->owner_items = items;
@@ -678,6 +678,67 @@ int ensure_items(Graph* g, cudaStream_t s) {
     g->num_owner_items = totals[0];
     g->num_hub_items = totals[1];
     g->owner_items_ready = true;
+    return GSP_OK;
+}
+
+// ---- the items of one owner range (owner-sharded scoring) ---------------------------------------------------------
+__global__ void flag_owned_kernel(int64_t count, const OwnerItem* __restrict__ items, int32_t lo, int32_t hi, int64_t* __restrict__ flags) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        flags[i] = items[i].owner >= lo && items[i].owner < hi;
+}
+
+__global__ void gather_owned_kernel(int64_t count, const OwnerItem* __restrict__ items, const int64_t* __restrict__ flags,
+                                    const int64_t* __restrict__ incl, OwnerItem* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        if (flags[i]) out[incl[i] - 1] = items[i];      // order kept: the id-window order of the full list
+}
+
+// Order-preserving filter of both item classes by owner range; cached for the last range used.
+int ensure_owned_items(Graph* g, int64_t owner_lo, int64_t owner_hi, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_items_mutex);
+    if (g->owned_items && g->owned_lo == owner_lo && g->owned_hi == owner_hi) return GSP_OK;
+    const int64_t total = g->num_owner_items + g->num_hub_items;
+    if (g->owned_items) {     // kernels of an earlier call (any stream) may still read the list of the previous range
+        GSP_CUDA_TRY(cudaDeviceSynchronize());
+        device_free(g->owned_items);
+    }
+    g->owned_items = nullptr;
+    g->num_owned_items = g->num_owned_hub_items = 0;
+    g->owned_lo = owner_lo;
+    g->owned_hi = owner_hi;
+    if (total == 0) return GSP_OK;
+    const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
+    Scratch<int64_t> flags, incl;
+    GSP_CUDA_TRY(flags.alloc(total, s));
+    GSP_CUDA_TRY(incl.alloc(total, s));
+    flag_owned_kernel<<<grid_for(total, 256), 256, 0, s>>>(total, items, (int32_t)owner_lo, (int32_t)owner_hi, flags.ptr);
+    GSP_CHECK_LAUNCH();
+    int64_t kept[2] = {0, 0};
+    const int64_t counts[2] = {g->num_owner_items, g->num_hub_items};
+    int64_t off = 0;
+    for (int c = 0; c < 2; ++c) {      // medium items first, hub items after them (each class scanned on its own)
+        if (counts[c] > 0) {
+            if (int rc = inclusive_sum_i64(flags.ptr + off, incl.ptr + off, counts[c], s)) return rc;
+            GSP_CUDA_TRY(cudaMemcpyAsync(&kept[c], incl.ptr + off + counts[c] - 1, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        }
+        off += counts[c];
+    }
+    GSP_CUDA_TRY(cudaStreamSynchronize(s));
+    OwnerItem* out = nullptr;
+    GSP_CUDA_TRY(device_alloc(&out, (size_t)(kept[0] + kept[1] ? kept[0] + kept[1] : 1) * sizeof(OwnerItem), s));
+    off = 0;
+    int64_t out_off = 0;
+    for (int c = 0; c < 2; ++c) {
+        if (counts[c] > 0) {
+            gather_owned_kernel<<<grid_for(counts[c], 256), 256, 0, s>>>(counts[c], items + off, flags.ptr + off, incl.ptr + off, out + out_off);
+            GSP_CHECK_LAUNCH();
+        }
+        off += counts[c];
+        out_off += kept[c];
+    }
+    g->owned_items = out;
+    g->num_owned_items = kept[0];
+    g->num_owned_hub_items = kept[1];
     return GSP_OK;
 }
 
@@ -742,12 +803,19 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     GSP_CUDA_TRY(counters.alloc(3, s));
     GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 3 * sizeof(unsigned long long), s));
     const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
+    int64_t num_medium = g->num_owner_items, num_hub = g->num_hub_items;
+    if (owner_lo > 0 || owner_hi < g->n) {   // owner-sharded call: only this range's items are claimed
+        if (int rc = ensure_owned_items(g, owner_lo, owner_hi, s)) return rc;
+        items = reinterpret_cast<const OwnerItem*>(g->owned_items);
+        num_medium = g->num_owned_items;
+        num_hub = g->num_owned_hub_items;
+    }
     // hubs first: their long work items should not land in the tail
     int hub_ctas = 2;
     const OwnerClass hub = hub_class_from_env(hub_ctas);
-    if (int rc = launch_class<kMode, kScatter>(hub, items + g->num_owner_items, g->num_hub_items, hub_ctas, g, r, node_w, inter, score,
+    if (int rc = launch_class<kMode, kScatter>(hub, items + num_medium, num_hub, hub_ctas, g, r, node_w, inter, score,
                                      jaccard, counters.ptr, s)) return rc;
-    if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, g->num_owner_items, 7, g, r, node_w, inter, score, jaccard,
+    if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, num_medium, 7, g, r, node_w, inter, score, jaccard,
                                      counters.ptr + 1, s)) return rc;
     const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
     warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter,

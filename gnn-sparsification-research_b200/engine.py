@@ -231,23 +231,6 @@ class DeviceGraph:
         xhat._gsp_packed = use_packed
         return xhat
 
-    def normalize_rows(self, x_rows: torch.Tensor, out: torch.Tensor) -> bool:
-        """Normalise a block of feature rows into `out` (same shape): the row-sharded form of `normalize_features`
-        (rows are independent, so blocks normalised on different ranks concatenate to the full result). Returns whether
-        the packed layout was used; the caller tags the assembled tensor with `_gsp_packed`."""
-        if x_rows.dim() != 2 or out.shape != x_rows.shape or out.dtype != x_rows.dtype:
-            raise ValueError("x_rows and out must be [rows, d] tensors of the same shape and dtype")
-        x_rows = x_rows.contiguous()
-        dim = x_rows.size(1)
-        packed = x_rows.dtype == torch.float32 and dim in (32, 64, 96, 128)
-        if packed:
-            fn = self._lib.gsp_featcos_normalize_f32_packed
-        else:
-            fn = self._lib.gsp_featcos_normalize_f32 if x_rows.dtype == torch.float32 else self._lib.gsp_featcos_normalize_f64
-        with torch.cuda.device(self.device):
-            check(fn(x_rows.size(0), dim, ptr(x_rows), dim, ptr(out), out.stride(0), self._stream()))
-        return packed
-
     def feature_cosine(self, xhat: torch.Tensor, e_begin=None, e_end=None, out=None):
         b, e = self._range(e_begin, e_end)
         score = self._empty(e - b, torch.float64) if out is None else out

@@ -10,8 +10,9 @@ The reference's drivers only know `GraphSparsifier(data, device)` + `compute_sco
                 1/N of the bytes per rank instead of N full uploads through the shared host;
   * scoring     Jaccard / Adamic-Adar owner-sharded with the exchange fused into the scoring kernel (peer stores into
                 NVLink-mapped symmetric memory; NCCL reduce-scatter when symmetric memory is unavailable), FeatCos /
-                degree on this rank's contiguous slice of canonical positions, feature normalisation row-sharded and
-                all-gathered once per graph, ApproxER column-sharded with an all-reduce of the partial sums;
+                degree on this rank's contiguous slice of canonical positions (the feature normalisation, 2.7 ms, is
+                replicated: gathering row-sharded results costs four times as much), ApproxER column-sharded with an
+                all-reduce of the partial sums;
   * selection   distributed radix select (16 KB histogram all-reduces), local compaction, kept `edge_index` slices
                 all-gathered in rank order (== position order);
   * outputs     `compute_scores` returns THIS RANK'S slice of the fp64 score vector and `return_mask=True` this rank's
@@ -35,7 +36,7 @@ import torch
 import torch.distributed as dist
 
 from . import sharding
-from .core import GraphSparsifier, _to_host
+from .core import GraphSparsifier, _copy_stream, _to_host
 from .engine import DeviceGraph, compact_edges, select_mask_sharded
 
 _PEER_CACHE: Dict[tuple, Optional[sharding.PeerScoreSlices]] = {}
@@ -76,8 +77,9 @@ def sharded_upload(t: torch.Tensor, dim: int, device, group) -> torch.Tensor:
         return full[:n]
     # [r, n] sharded along the columns (edge_index): one in-place gather per row keeps every row contiguous
     full = torch.empty((t.size(0), length * world), dtype=t.dtype, device=device)
-    full[:, lo:hi].copy_(t[:, lo:hi], non_blocking=True)
     for r in range(t.size(0)):
+        # row by row: each piece is contiguous on both sides (a strided host slice takes torch's slow staged copy: 6 GB/s)
+        full[r, lo:hi].copy_(t[r, lo:hi], non_blocking=True)
         dist.all_gather_into_tensor(full[r], full[r, rank * length:(rank + 1) * length], group=group)
     return full[:, :n] if length * world == n else full[:, :n].contiguous()
 
@@ -87,12 +89,25 @@ def sharded_to_device(data, device, group):
     each rank's PCIe link carries 1/N of `edge_index` and of every per-node tensor."""
     out = data.__class__.__new__(data.__class__)
     items = list(data._items()) if hasattr(data, "_items") else list(data.__dict__.items())
-    for key, value in items:
+    moved = {}
+    for key, value in sorted(items, key=lambda kv: kv[0] != "edge_index"):     # stable: edge_index first
         if key.startswith("_gsp_"):
             continue
         if torch.is_tensor(value):
+            was_host = not value.is_cuda
             value = sharded_upload(value, 1 if key == "edge_index" else 0, device, group)
-        out.__dict__[key] = value
+            if key == "edge_index" and was_host and value.is_cuda:
+                # like Data.to(non_blocking=True): the sparsifier builds the CSR behind this event, on a side stream, while
+                # the (larger) feature slices are still crossing PCIe and NVLink
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream(value.device))
+                moved["_gsp_edge_index_ready"] = event
+        moved[key] = value
+    for key, _ in items:                                                        # keep the attribute order of the source
+        if key in moved:
+            out.__dict__[key] = moved[key]
+    if "_gsp_edge_index_ready" in moved:
+        out.__dict__["_gsp_edge_index_ready"] = moved["_gsp_edge_index_ready"]
     return out
 
 
@@ -112,6 +127,8 @@ class ShardedGraphSparsifier(GraphSparsifier):
 
     # ------------------------------------------------------------------------------ layout
     def _build_graph(self) -> DeviceGraph:
+        if self._graph is None and self.data.edge_index.is_cuda:
+            return super()._build_graph()      # (side-stream build behind the arrival event of `sharded_to_device`)
         if self._graph is None:
             dev = self._cuda_device()
             ei = self.data.edge_index
@@ -171,23 +188,11 @@ class ShardedGraphSparsifier(GraphSparsifier):
         self._slices[metric] = self._local(s)
 
     def _normalized_features(self) -> torch.Tensor:
-        """xhat replica: rows [n_lo, n_hi) normalised here, slices all-gathered once per graph (reference metrics.py:344-346)."""
+        """Normalised feature replica (reference metrics.py:344-346). Computed on every rank from its replica of `x`:
+        2.7 ms at 16.7 M x 128 fp32, against ~11 ms for all-gathering row-sharded results over NVLink (measured on 8 GPUs:
+        the gather moves 7/8 of 8.6 GB to every rank)."""
         if self._xhat is None:
-            g = self.graph
-            x = self.data.x
-            n = self.num_nodes
-            length = (n + self._world - 1) // self._world
-            lo, hi = min(self._rank * length, n), min((self._rank + 1) * length, n)
-            if not x.is_cuda:
-                x = sharded_upload(x, 0, g.device, self._group)
-            if x.dtype not in (torch.float32, torch.float64):
-                x = x.to(torch.float64)
-            x = x.to(g.device).contiguous()
-            full = torch.empty((length * self._world, x.size(1)), dtype=x.dtype, device=g.device)
-            packed = g.normalize_rows(x[lo:hi], out=full[lo:hi])
-            dist.all_gather_into_tensor(full, full[self._rank * length:(self._rank + 1) * length], group=self._group)
-            self._xhat = full[:n]
-            self._xhat._gsp_packed = packed
+            self._xhat = self.graph.normalize_features(self.data.x)
         return self._xhat
 
     def _slice_scores(self, key: str) -> torch.Tensor:
@@ -241,16 +246,27 @@ class ShardedGraphSparsifier(GraphSparsifier):
             return super()._device_scores(metric)
         return self._gathered(self._normalize_metric_name(metric))
 
-    def prefetch_scores(self, metrics) -> None:
-        """Announce the metric list: Jaccard and Adamic-Adar requested together come from ONE streaming pass per rank."""
+    def prefetch_scores(self, metrics, to_host: bool = False) -> None:
+        """Announce the metric list: Jaccard and Adamic-Adar requested together come from ONE streaming pass per rank;
+        `to_host=True` queues the read-back of every slice behind its kernel (copy stream, page-locked buffers)."""
         if not self.sharded:
-            return super().prefetch_scores(metrics)
+            return super().prefetch_scores(metrics, to_host)
         keys = [self._normalize_metric_name(m) for m in metrics]
         pending = [k for k in keys if k not in self._slices and k not in self._score_cache]
         if "jaccard" in pending and "adamic_adar" in pending:
             self._neighbourhood_slices(True, True)
         for k in keys:
-            self._slice_scores(k)
+            t = self._slice_scores(k)
+            if to_host and not self.gather_outputs and ("local", k) not in self._host_cache() and k not in self._host_pending:
+                cs = _copy_stream(t.device)
+                cs.wait_stream(torch.cuda.current_stream(t.device))
+                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                with torch.cuda.stream(cs):
+                    host.copy_(t, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(cs)
+                t.record_stream(cs)
+                self._host_pending[k] = (host, done)
 
     def compute_scores(self, metric: str) -> np.ndarray:
         """float64 ndarray: this rank's slice (`local_range`), or the full vector with `gather_outputs=True`."""
@@ -259,8 +275,13 @@ class ShardedGraphSparsifier(GraphSparsifier):
         key = self._normalize_metric_name(metric)
         cache_key = key if self.gather_outputs else ("local", key)
         if cache_key not in self._host_cache():
-            src = self._gathered(key) if self.gather_outputs else self._slice_scores(key)
-            self._host_cache()[cache_key] = _to_host(src).numpy()
+            if not self.gather_outputs and key in self._host_pending:
+                host, done = self._host_pending.pop(key)
+                done.synchronize()
+                self._host_cache()[cache_key] = host.numpy()
+            else:
+                src = self._gathered(key) if self.gather_outputs else self._slice_scores(key)
+                self._host_cache()[cache_key] = _to_host(src).numpy()
         return self._host_cache()[cache_key]
 
     def _host_cache(self) -> dict:

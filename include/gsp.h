@@ -62,6 +62,17 @@ int gsp_version(void);
 const char* gsp_last_error(void);
 /* Number of CUDA kernels this library has launched in the process so far (monotonic; for benchmarks). */
 uint64_t gsp_launch_count(void);
+/* Device-memory hook. Before the first graph is created a host may hand the library its own allocator (the Python
+ * layer passes torch's caching allocator): every device byte the library holds — graph arrays, lazily built side
+ * structures, scratch — then comes from it, stays visible to the host framework and is recycled across graph builds
+ * instead of paying cudaMalloc / cudaFree of gigabytes each time. alloc(bytes, device, stream) returns a device pointer
+ * usable on `stream` (NULL on failure); free(ptr) may recycle the block for later allocations on that stream
+ * (cudaFreeAsync semantics); gsp_graph_destroy synchronises the device first. Pass NULL, NULL (the default) for
+ * cudaMalloc / cudaFree + the private scratch pool below. Not to be changed while library-owned memory is live. */
+typedef void* (*gsp_alloc_fn)(size_t bytes, int device, void* stream);
+typedef void (*gsp_free_fn)(void* ptr);
+int gsp_set_allocator(gsp_alloc_fn alloc_fn, gsp_free_fn free_fn);
+
 /* The library allocates its scratch from a private stream-ordered pool per device that keeps at most GSP_SCRATCH_KEEP_MB
  * (default 1024) of freed memory across synchronisation points; this hands all of it back to the driver (synchronises
  * the device). */

@@ -12,7 +12,7 @@ for t in "${tags[@]}"; do
   python - "$t" <<'PY'
 import json, sys
 d = json.load(open(f"gpurun_out/ab_{sys.argv[1]}.json"))
-print(sys.argv[1], round(d["ms_per_step"], 2), {k: round(v["ms"], 2) for k, v in d["per_method"].items()})
+print(sys.argv[1], round(d["ms_per_step"], 2), {k: round(v["ms"], 2) for k, v in d["roofline"]["per_method"].items()})
 PY
 done
 done

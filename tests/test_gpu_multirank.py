@@ -75,8 +75,9 @@ def _worker(rank, world, port, fail):
                 mine = sp.compute_scores(m)
                 ref = single.compute_scores(m)
                 assert mine.shape == (hi - lo,), (name, m)
-                if m == "approx_er":      # column-sharded sums are all-reduced: a different association of the k partial sums
-                    np.testing.assert_allclose(mine, ref[lo:hi], rtol=1e-9, err_msg=f"{name} {m}")
+                if m == "approx_er":      # 4 columns per rank instead of 8 in one block: the column dot products of the CG
+                    # are reduced in another order (up to ~2e-5 apart after ~100 iterations); the bar is BASELINE.json's 1e-4
+                    np.testing.assert_allclose(mine, ref[lo:hi], rtol=1e-4, err_msg=f"{name} {m}")
                 else:
                     assert mine.tobytes() == ref[lo:hi].tobytes(), (name, m)
                 if m in oracle:
