@@ -13,6 +13,7 @@
 // its sorted position). Column reductions are two-stage and deterministic (fixed block order), so a
 // run is bit-reproducible; they are NOT BLAS ddot's order — ApproxER parity is the 1e-4 relative
 // tolerance BASELINE.json states, not bit equality.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -60,6 +61,50 @@ __device__ __forceinline__ LaneMap lane_map(int k) {
     return m;
 }
 
+// ---- projection entries generated where they are used ----------------------------------------------------------------
+// R[e, c] ~ N(0, 1) / sqrt(k) as a pure function of (seed, e, c): Philox4x32-10 keyed by the seed with the counter
+// (e, c), two 53-bit uniforms, Box-Muller. Both endpoints of an edge evaluate the same entry, so the [m, k] fp64 matrix
+// (31.7 GB at the products shape with k = 64) is never materialised; gsp_philox_projection writes the same entries out for
+// tests and for callers that want to inspect the matrix.
+struct Projection {
+    const double* R;     // explicit matrix (parity mode: the reference's NumPy PCG64 draws), or nullptr
+    int64_t ldr;
+    uint64_t seed;       // generated mode
+    int32_t col0;        // global index of local column 0 (column sharding)
+    double scale;        // 1 / sqrt(total columns)
+};
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+
+__device__ __forceinline__ double philox_normal(uint64_t seed, int64_t e, int32_t c) {
+    uint32_t ctr[4] = {(uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)c, 0x6a09e667u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(ctr, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    // (0, 1) uniforms from 53 random bits each
+    const double u1 = ((double)((((uint64_t)ctr[0] << 32) | ctr[1]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)((((uint64_t)ctr[2] << 32) | ctr[3]) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__device__ __forceinline__ double projection_entry(const Projection& pr, int64_t e, int32_t c) {
+    return pr.R ? __ldg(pr.R + e * pr.ldr + c) : philox_normal(pr.seed, e, pr.col0 + c) * pr.scale;
+}
+
+__global__ void philox_projection_kernel(int64_t m, int32_t k, Projection pr, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m * k; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = projection_entry(pr, i / k, (int32_t)(i % k));
+}
+
 // Y[u, c] = sum over incident undirected edges e (ascending e) of +-R[e, c]   (metrics.py:260-275).
 // Same row-segment work items as the SpMM (a hub row's 10^5 incident edges are spread over many warps); rows longer
 // than one segment are finished by project_combine_kernel in segment order.
@@ -72,7 +117,7 @@ constexpr int kSeg = 512;
 __global__ void __launch_bounds__(kThreads)
 project_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
                const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-               const int32_t* __restrict__ und_id, const double* __restrict__ R, int64_t ldr, int k,
+               const int32_t* __restrict__ und_id, Projection pr, int k,
                double* __restrict__ Y, double* __restrict__ segpart) {
     const LaneMap m = lane_map(k);
     const int64_t warp = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
@@ -90,7 +135,7 @@ project_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64
             if (e < 0) continue;                                    // self loop / unmatched direction
             const int32_t v = __ldg(indices + p);
             if (m.col_ok) {
-                const double r = __ldg(R + (int64_t)e * ldr + m.c);
+                const double r = projection_entry(pr, e, m.c);
                 acc = (u < v) ? __dadd_rn(acc, r) : __dsub_rn(acc, r);   // +1 * r / -1 * r are exact
             }
         }
@@ -152,12 +197,21 @@ init_kernel(int64_t n, int k, const double* __restrict__ r, double* __restrict__
 }
 
 // Column finalisation at the TOP of iteration `it`: rr = sum of partials; convergence test; beta.
+// Sum of one column's block partials by one warp: lane l adds blocks l, l + 32, ... in order, then a fixed xor tree —
+// deterministic, and ~40 dependent adds instead of the ~1200 of a single thread (18 us per launch, twice per iteration).
+__device__ __forceinline__ double column_sum(const double* __restrict__ partial, int nblocks, int k, int c) {
+    double s = 0.0;
+    for (int b = lane_id(); b < nblocks; b += kWarp) s = __dadd_rn(s, partial[(int64_t)b * k + c]);
+    for (int off = kWarp / 2; off; off >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, off));
+    return s;
+}
+
 __global__ void top_kernel(int k, int nblocks, const double* __restrict__ partial, CgColumns cg, double rtol, int it,
                            int* __restrict__ num_active) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x >> 5);   // one warp per column
     if (c >= k) return;
-    double rr = 0.0;
-    for (int b = 0; b < nblocks; ++b) rr = __dadd_rn(rr, partial[(int64_t)b * k + c]);
+    const double rr = column_sum(partial, nblocks, k, c);
+    if (lane_id() != 0) return;
     if (it < 0) {  // initialisation: rr = b.b
         const double bnrm = sqrt(rr);
         cg.atol[c] = __dmul_rn(rtol, bnrm);                        // atol = max(0, rtol*||b||)
@@ -273,8 +327,8 @@ spmm_dot_kernel(const SegItem* __restrict__ items, int64_t num_items, const int6
 // list of a row is read once per 64 columns instead of once per 32 and half as many load instructions are issued.
 // The neighbour ids of the next four-deep step are fetched while the current step's gathers are in flight (the first
 // version serialised "load ids -> gather p -> consume" and ran at 30 % occupancy / 12 % of the L2->SM path, ncu).
-template <bool kHasData, bool kPacked>
-__global__ void __launch_bounds__(kThreads, 4)
+template <bool kHasData, bool kPacked, int kBlocks, int kDepth>
+__global__ void __launch_bounds__(kThreads, kBlocks)
 spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int64_t* __restrict__ seg_incl,
                  const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ data,
                  const double* __restrict__ diag, int k, const double* __restrict__ p, double* __restrict__ q,
@@ -297,29 +351,29 @@ spmm_dot2_kernel(const SegItem* __restrict__ items, int64_t num_items, const int
             const int64_t p0 = item_ok ? row0 + (int64_t)seg * kSeg : 0;
             const int64_t p1 = item_ok ? min(p0 + kSeg, row1) : 0;
             const bool single = row1 - row0 <= kSeg;
-            int32_t jn[4];
+            int32_t jn[kDepth];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) jn[u] = p0 + u < p1 ? __ldg(indices + p0 + u) : -1;
+            for (int u = 0; u < kDepth; ++u) jn[u] = p0 + u < p1 ? __ldg(indices + p0 + u) : -1;
             double2 pi = make_double2(0.0, 0.0);
             if (single && item_ok) pi = *reinterpret_cast<const double2*>(p + i * (int64_t)k + c);
             const double di = diag[i];
             const double d0 = __dmul_rn(di, pi.x), d1 = __dmul_rn(di, pi.y);
             double s0 = 0.0, s1 = 0.0;
             bool placed = !single;
-            for (int64_t t0 = p0; kPacked ? __any_sync(0xffffffffu, t0 < p1) : t0 < p1; t0 += 4) {   // packed row slots differ in length
-                int32_t j[4];
-                double2 pj[4];
-                double a[4];
+            for (int64_t t0 = p0; kPacked ? __any_sync(0xffffffffu, t0 < p1) : t0 < p1; t0 += kDepth) {   // packed row slots differ in length
+                int32_t j[kDepth];
+                double2 pj[kDepth];
+                double a[kDepth];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kDepth; ++u) {
                     j[u] = jn[u];
                     pj[u] = j[u] >= 0 ? __ldg(reinterpret_cast<const double2*>(p + (int64_t)j[u] * k + c)) : make_double2(0.0, 0.0);
                     a[u] = (kHasData && j[u] >= 0) ? __ldg(data + t0 + u) : 1.0;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) jn[u] = t0 + 4 + u < p1 ? __ldg(indices + t0 + 4 + u) : -1;   // next step's ids
+                for (int u = 0; u < kDepth; ++u) jn[u] = t0 + kDepth + u < p1 ? __ldg(indices + t0 + kDepth + u) : -1;   // next step's ids
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kDepth; ++u) {
                     if (j[u] < 0) break;
                     if (j[u] == i) {
                         if (!placed) { s0 = __dadd_rn(s0, d0); s1 = __dadd_rn(s1, d1); placed = true; }
@@ -396,10 +450,10 @@ __global__ void seg_fill_kernel(int64_t n, const int64_t* __restrict__ incl, Seg
 }
 
 __global__ void alpha_kernel(int k, int nblocks, const double* __restrict__ partial, CgColumns cg) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x / kWarp) + (threadIdx.x >> 5);   // one warp per column
     if (c >= k || !cg.active[c]) return;
-    double pq = 0.0;
-    for (int b = 0; b < nblocks; ++b) pq = __dadd_rn(pq, partial[(int64_t)b * k + c]);
+    const double pq = column_sum(partial, nblocks, k, c);
+    if (lane_id() != 0) return;
     cg.alpha[c] = __ddiv_rn(cg.rho[c], pq);
     cg.iters[c] += 1;
 }
@@ -522,14 +576,13 @@ int ensure_und_id(Graph* g, void* stream) {
 
 using namespace gsp;
 
-GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_t ldr, int32_t k, int32_t max_iters,
-                                  double rtol, double reg, int64_t e_begin, int64_t e_end, double* d_partial,
-                                  int32_t* d_iters, void* stream) {
+static int approx_er_partial(const gsp_graph* gg, const Projection& pr, int32_t k, int32_t max_iters, double rtol, double reg,
+                             int64_t e_begin, int64_t e_end, double* d_partial, int32_t* d_iters, void* stream) {
     GSP_REQUIRE(gg != nullptr, "graph is NULL");
     Graph* g = const_cast<Graph*>(reinterpret_cast<const Graph*>(gg));
     GSP_REQUIRE(e_begin >= 0 && e_begin <= e_end && e_end <= g->nnz, "edge range outside [0, nnz]");
-    GSP_REQUIRE(k >= 1 && max_iters >= 0 && ldr >= k, "bad k / max_iters / ldr");
-    GSP_REQUIRE(d_R && (e_end == e_begin || d_partial), "NULL argument");
+    GSP_REQUIRE(k >= 1 && max_iters >= 0, "bad k / max_iters");
+    GSP_REQUIRE(e_end == e_begin || d_partial, "NULL argument");
     if (!g->symmetric) {
         set_error("approximate effective resistance needs a symmetric adjacency pattern (reference metrics.py:208-209)");
         return GSP_ERR_UNSUPPORTED;
@@ -540,9 +593,14 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     if (int rc = ensure_segments(g, s)) return rc;
     const int64_t extra_segments = g->num_seg_items - n;   // > 0 when some row is longer than kSeg
 
+    // Four-deep gathers at 4 CTAs / SM. Measured on the products shape (k = 64): 9.8-10.2 ms per CG iteration; eight-deep
+    // gathers at 3 CTAs / SM 11.2 ms, four-deep at 5 CTAs / SM (48 registers, spills) 11.0 ms — more loads in flight do not
+    // help: the gather moves nnz * 8k = 63 GB from L2 to the SMs per product (ncu: 25 GB of it from DRAM, L2 hit rate 48 %),
+    // ~6.5 TB/s through the L2 fabric.
+    const int spmm_ctas = 8;
     const int strips = k >= kWarp ? (k + kWarp - 1) / kWarp : 1;   // k < 32: several rows per warp instead of strips
     // row blocks: enough CTAs for >= 8 per SM over all strips, at most one warp-row each
-    int64_t row_blocks = (static_cast<int64_t>(kNumSMs) * 8 + strips - 1) / strips;
+    int64_t row_blocks = (static_cast<int64_t>(kNumSMs) * spmm_ctas + strips - 1) / strips;
     const int64_t max_rb = (n + kWarps - 1) / kWarps;
     if (row_blocks > max_rb) row_blocks = max_rb;
     if (row_blocks < 1) row_blocks = 1;
@@ -572,8 +630,8 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     diag_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, g->indptr, g->indices, g->data, reg, diag.ptr);
     GSP_CHECK_LAUNCH();
     const SegItem* seg_items = reinterpret_cast<const SegItem*>(g->seg_items);
-    project_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->und_id, d_R,
-                                               ldr, k, r.ptr, segpart.ptr);
+    project_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->und_id, pr,
+                                               k, r.ptr, segpart.ptr);
     GSP_CHECK_LAUNCH();
     if (extra_segments > 0) {
         project_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, k, r.ptr, segpart.ptr);
@@ -581,7 +639,7 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
     }
     init_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, x.ptr, partial.ptr);
     GSP_CHECK_LAUNCH();
-    const int col_blocks = (k + 127) / 128;
+    const int col_blocks = (k + 3) / 4;   // 128 threads = four columns (one warp each)
     top_kernel<<<col_blocks, 128, 0, s>>>(k, nb, partial.ptr, cg, rtol, -1, num_active);
     GSP_CHECK_LAUNCH();
 
@@ -600,7 +658,7 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
         if (k % 64 == 0 || pow2_small) {   // two columns per lane: 64-column strips, or 64/k rows per warp when k < 64
             const dim3 grid64((unsigned)row_blocks, (unsigned)(k >= 64 ? k / 64 : 1));
 #define GSP_SPMM2(HAS_DATA, PACKED)                                                                                          \
-    spmm_dot2_kernel<HAS_DATA, PACKED><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, \
+    spmm_dot2_kernel<HAS_DATA, PACKED, 4, 4><<<grid64, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, \
                                                                   g->data, diag.ptr, k, p.ptr, q.ptr, segpart.ptr, cg.active,    \
                                                                   partial.ptr)
             if (g->data) { if (pow2_small) GSP_SPMM2(true, true); else GSP_SPMM2(true, false); }
@@ -627,6 +685,33 @@ GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_
                                                                          d_partial);
         GSP_CHECK_LAUNCH();
     }
+    return GSP_OK;
+}
+
+GSP_API int gsp_approx_er_partial(const gsp_graph* gg, const double* d_R, int64_t ldr, int32_t k, int32_t max_iters,
+                                  double rtol, double reg, int64_t e_begin, int64_t e_end, double* d_partial,
+                                  int32_t* d_iters, void* stream) {
+    GSP_REQUIRE(d_R != nullptr && ldr >= k, "projection matrix is NULL or ldr < k");
+    const Projection pr{d_R, ldr, 0, 0, 1.0};
+    return approx_er_partial(gg, pr, k, max_iters, rtol, reg, e_begin, e_end, d_partial, d_iters, stream);
+}
+
+GSP_API int gsp_approx_er_partial_philox(const gsp_graph* gg, uint64_t seed, int32_t col_begin, int32_t k, int32_t k_total,
+                                         int32_t max_iters, double rtol, double reg, int64_t e_begin, int64_t e_end,
+                                         double* d_partial, int32_t* d_iters, void* stream) {
+    GSP_REQUIRE(col_begin >= 0 && k >= 1 && k_total >= col_begin + k, "bad column range");
+    const Projection pr{nullptr, 0, seed, col_begin, 1.0 / sqrt((double)k_total)};
+    return approx_er_partial(gg, pr, k, max_iters, rtol, reg, e_begin, e_end, d_partial, d_iters, stream);
+}
+
+GSP_API int gsp_philox_projection(uint64_t seed, int64_t m, int32_t col_begin, int32_t k, int32_t k_total, double* d_R,
+                                  void* stream) {
+    GSP_REQUIRE(m >= 0 && col_begin >= 0 && k >= 1 && k_total >= col_begin + k, "bad sizes");
+    if (m == 0) return GSP_OK;
+    GSP_REQUIRE(d_R != nullptr, "d_R is NULL");
+    const Projection pr{nullptr, 0, seed, col_begin, 1.0 / sqrt((double)k_total)};
+    philox_projection_kernel<<<grid_for(m * k, 256), 256, 0, as_stream(stream)>>>(m, k, pr, d_R);
+    GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
 

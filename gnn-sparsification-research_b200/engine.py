@@ -258,6 +258,26 @@ class DeviceGraph:
                                                   float(rtol), float(reg), b, e, ptr(out), ptr(iters), self._stream()))
         return (out, iters) if return_iters else out
 
+    def approx_er_partial_philox(self, seed: int, col_begin: int, k: int, k_total: int, max_iters=500, rtol=1e-6, reg=1e-6,
+                                 return_iters=False):
+        """Partial resistance sums over the projection columns [col_begin, col_begin + k) of the `k_total`-column Philox
+        matrix of `seed`, generated inside the projection kernel (no [m, k] matrix in memory)."""
+        out = self._empty(self.nnz, torch.float64)
+        iters = self._empty(k, torch.int32) if return_iters else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_approx_er_partial_philox(self._handle, int(seed) & (2 ** 64 - 1), int(col_begin), int(k), int(k_total),
+                                                         int(max_iters), float(rtol), float(reg), 0, self.nnz, ptr(out), ptr(iters),
+                                                         self._stream()))
+        return (out, iters) if return_iters else out
+
+    def philox_projection(self, seed: int, col_begin: int, k: int, k_total: int) -> torch.Tensor:
+        """fp64 [num_undirected, k]: the entries `approx_er_partial_philox` draws, written out (tests, inspection)."""
+        r = torch.empty((self.num_undirected, k), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_philox_projection(int(seed) & (2 ** 64 - 1), self.num_undirected, int(col_begin), int(k), int(k_total),
+                                                  ptr(r), self._stream()))
+        return r
+
     def er_finalize(self, partial: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(self.device):
             check(self._lib.gsp_er_finalize(ptr(partial), partial.numel(), self._stream()))

@@ -73,8 +73,9 @@ def _approx_er_on_graph(g: DeviceGraph, epsilon=0.3, seed=42, max_cg_iters=500, 
                         projection=None, group=None, return_iters=False):
     """ApproxER on a device graph. `projection`: None / "numpy" (the reference's PCG64 matrix, generated on the
     host exactly like metrics.py:232,272), "device" (torch Philox normals on the GPU, same distribution,
-    no host work), or an explicit [m, k] array/tensor. With a process `group` the projection columns are
-    split over its ranks and the per-edge partial sums are all-reduced (NCCL)."""
+    no host work: Philox entries generated inside the projection kernel, the [m, k] matrix is never materialised), or an
+    explicit [m, k] array/tensor. With a process `group` the projection columns are split over its ranks and the per-edge
+    partial sums are all-reduced (NCCL)."""
     m = g.num_undirected
     nnz = g.nnz
     dev = g.device
@@ -88,9 +89,7 @@ def _approx_er_on_graph(g: DeviceGraph, epsilon=0.3, seed=42, max_cg_iters=500, 
         if k is None:
             k = jl_dimension(g.num_nodes, epsilon)
         if projection == "device":
-            gen = torch.Generator(device=dev)
-            gen.manual_seed(int(seed))
-            R = torch.randn((m, k), dtype=torch.float64, device=dev, generator=gen) / np.sqrt(k)
+            R = None
         else:
             R = torch.from_numpy(np.random.default_rng(seed).standard_normal((m, k)) / np.sqrt(k))
     rank, world = 0, 1
@@ -103,10 +102,13 @@ def _approx_er_on_graph(g: DeviceGraph, epsilon=0.3, seed=42, max_cg_iters=500, 
     kb = _column_block(g.num_nodes, max(c_hi - c_lo, 1))
     for c0 in range(c_lo, c_hi, kb):
         c1 = min(c0 + kb, c_hi)
-        block = R[:, c0:c1]
-        if not block.is_cuda:
-            block = block.contiguous().to(dev, non_blocking=True)
-        part, it = g.approx_er_partial(block, max_cg_iters, cg_tol, 1e-6, return_iters=True)
+        if R is None:
+            part, it = g.approx_er_partial_philox(seed, c0, c1 - c0, k, max_cg_iters, cg_tol, 1e-6, return_iters=True)
+        else:
+            block = R[:, c0:c1]
+            if not block.is_cuda:
+                block = block.contiguous().to(dev, non_blocking=True)
+            part, it = g.approx_er_partial(block, max_cg_iters, cg_tol, 1e-6, return_iters=True)
         total += part
         iters[c0:c1] = it
     if group is not None and world > 1:

@@ -190,6 +190,15 @@ int gsp_featcos_f64(const gsp_graph* g, const double* d_xhat, int32_t dim, int64
 int gsp_approx_er_partial(const gsp_graph* g, const double* d_R, int64_t ldr, int32_t k, int32_t max_iters,
                           double rtol, double reg, int64_t e_begin, int64_t e_end, double* d_partial,
                           int32_t* d_iters, void* stream);
+/* The same with the projection generated where it is used (throughput mode): R[e, c] = N(0,1) / sqrt(k_total) as a pure
+ * function of (seed, e, col_begin + c) — Philox4x32-10, Box-Muller — so the fp64 [m, k] matrix (31.7 GB at the
+ * products shape with k = 64) is never materialised. Columns [col_begin, col_begin + k) of k_total: ranks that split the
+ * columns draw from one matrix. gsp_philox_projection writes those entries out (fp64 [m, k] row-major): feeding them to
+ * gsp_approx_er_partial gives bit-identical results (tests). Not the reference's PCG64 stream: parity runs pass d_R. */
+int gsp_approx_er_partial_philox(const gsp_graph* g, uint64_t seed, int32_t col_begin, int32_t k, int32_t k_total,
+                                 int32_t max_iters, double rtol, double reg, int64_t e_begin, int64_t e_end,
+                                 double* d_partial, int32_t* d_iters, void* stream);
+int gsp_philox_projection(uint64_t seed, int64_t m, int32_t col_begin, int32_t k, int32_t k_total, double* d_R, void* stream);
 int gsp_er_finalize(double* d_score, int64_t count, void* stream);
 
 /* ---- metric backbone ---------------------------------------------------------------
