@@ -472,7 +472,15 @@ class GraphSparsifier:
             raise IndexError(f"index {self.num_edges - 1} is out of bounds for axis 0 with size {scores.numel()}")
         num_keep = int(self.num_edges * retention_ratio)
         src = self._ei_dev[0]
-        mask, marked = degree_aware_guarantee(src, scores, self.num_nodes, max(int(min_edges_per_node), 0))
+        m = int(min_edges_per_node)
+        if m < 0:
+            raise ValueError("min_edges_per_node must be >= 0")   # (the reference's `[-k:]` with k < 0 is an accident, not an API)
+        if m == 0:
+            # reference core.py:432-434: `argsort(...)[-0:]` is the whole array, so EVERY incident edge is guaranteed and
+            # the budget is exceeded: the full graph comes back
+            mask = torch.ones(self.num_edges, dtype=torch.uint8, device=scores.device)
+            return self._finish(mask, self.num_edges, return_mask)
+        mask, marked = degree_aware_guarantee(src, scores, self.num_nodes, m)
         guaranteed = int(marked.item())            # one 8-byte host read: the output size depends on it
         kept = guaranteed
         if guaranteed < num_keep:

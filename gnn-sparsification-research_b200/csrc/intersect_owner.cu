@@ -397,7 +397,29 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
         // Branch-free rounds of two groups: ids below the tile are not in its table, so both groups are probed and
         // accumulated wherever the boundary falls; the in-tile ids are a prefix of the 64 visited (ids descend).
         const bool no_stash = table.stash_n == 0;
-        for (;;) {
+        if (no_stash) {
+            // While the 128 ids below the cursor all lie inside the tile (ids descend: the lowest of them decides, one
+            // uniform load from the line the round reads anyway) they take the bound-free four-group round of the lowest
+            // tile: ~36 instead of ~53 instructions per 32 ids (ncu source page, round 2); only the ragged end of the piece
+            // goes through the two-group rounds below.
+            constexpr int D = 4;
+            while (cursor >= D * kWarp && __ldg(row_w + cursor - D * kWarp) >= lo_id) {
+                const int top = cursor - 1 - lane;
+                int32_t x[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = __ldg(row_w + top - k * kWarp);
+                bool hit[D];
+                double w[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) hit[k] = cuckoo_hit(table, x[k]);
+#pragma unroll
+                for (int k = 0; k < D; ++k) w[k] = hit[k] ? __ldg(node_w + x[k]) : 0.0;
+#pragma unroll
+                for (int k = 0; k < D; k += 2) accumulate_hits2(hit[k], w[k], hit[k + 1], w[k + 1], queue, acc, nh);
+                cursor -= D * kWarp;
+            }
+        }
+        while (cursor > 0) {
             const int top = cursor - 1 - lane;
             const int32_t x0 = top >= 0 ? __ldg(row_w + top) : INT_MIN;
             const int32_t x1 = top - kWarp >= 0 ? __ldg(row_w + top - kWarp) : INT_MIN;
@@ -413,7 +435,7 @@ __device__ __forceinline__ int stream_down(const int32_t* __restrict__ row_w, in
             const int used = __popc(__ballot_sync(0xffffffffu, x0 >= lo_id)) + __popc(__ballot_sync(0xffffffffu, x1 >= lo_id));
             accumulate_hits2(h0, w0, h1, w1, queue, acc, nh);
             cursor -= used;
-            if (used < 2 * kWarp || cursor <= 0) break;   // ran off the tile or the row
+            if (used < 2 * kWarp) break;   // ran off the tile (or the row: cursor == 0)
         }
     } else {
         bool done = false;
@@ -826,20 +848,26 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
 
 }  // namespace
 
-// Estimated streaming work of every owner: ids of the owned neighbours' rows + a constant per neighbour.
+// Estimated work of every owner, in streamed-id equivalents: the ids of the owned neighbours' rows + a constant per
+// neighbour; the rows of an owner that needs several hash tiles are chopped into one piece per tile (a fixed cost per
+// piece) and their ids go through the costlier bounded rounds. Calibrated on 4 GPUs (R-MAT scale 24, fused pass): with
+// the plain id count the rank that holds the largest hubs ran 54.8 ms against 46.6-47.6 ms for the others.
 __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                   double* __restrict__ cost) {
     const int lane = lane_id();
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int hub_tile = tile_ids_for(kHubClass.slots);
     for (int64_t o = warp; o < n; o += nwarps) {
         const int64_t a0 = indptr[o], a1 = indptr[o + 1];
         const int d_o = (int)(a1 - a0);
+        const int tiles = d_o > hub_tile ? (d_o + hub_tile - 1) / hub_tile : 1;
+        const double per_id = tiles > 1 ? 1.3 : 1.0, per_row = 16.0 + (tiles > 1 ? 24.0 * tiles : 0.0);
         double c = 0.0;
         for (int64_t p = a0 + lane; p < a1; p += kWarp) {
             const int32_t w = __ldg(indices + p);
             const int d_w = (int)(__ldg(indptr + w + 1) - __ldg(indptr + w));
-            c += other_owns(d_w, w, d_o, (int32_t)o) ? 2.0 : (double)d_w + 16.0;
+            c += other_owns(d_w, w, d_o, (int32_t)o) ? 2.0 : per_id * (double)d_w + per_row;
         }
         for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
         if (lane == 0) cost[o] = c + (d_o ? 8.0 : 0.0);

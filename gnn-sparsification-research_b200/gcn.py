@@ -85,8 +85,12 @@ class GcnPropagation:
                                              stream_ptr(self.device)))
 
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Forward only: the result is written by the kernel into a plain tensor and carries no autograd graph."""
         if x.dim() != 2 or x.size(0) != self.num_nodes:
             raise ValueError("x must have shape [num_nodes, dim]")
+        if x.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("GcnPropagation is inference-only (no backward pass): call it under torch.no_grad() or on a "
+                               "detached tensor; inside a trained model it would silently cut the gradient to x")
         x = x.to(device=self.device, dtype=torch.float32)
         if x.stride(1) != 1:
             x = x.contiguous()

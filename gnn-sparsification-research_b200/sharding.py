@@ -145,13 +145,18 @@ def owner_sharded_scores_p2p(graph, metric: str, peer: PeerScoreSlices, node_ran
 
 
 def owner_sharded_jaccard_adamic_adar_p2p(graph, peer_jaccard: PeerScoreSlices, peer_adamic_adar: PeerScoreSlices,
-                                          node_range: Tuple[int, int], node_weights=None):
+                                          node_range: Tuple[int, int], node_weights=None, kernel_events=None):
     """Fused pass + fused exchange: one streaming kernel per rank stores both scores of every pair it owns straight into
-    the owning ranks' slices (two symmetric-memory buffers)."""
+    the owning ranks' slices (two symmetric-memory buffers). `kernel_events`: an optional pair of CUDA events recorded
+    around this rank's kernels alone (between the barriers), for the per-rank load-balance figure of the benchmark."""
     peer_jaccard.barrier()
     peer_adamic_adar.barrier()
+    if kernel_events is not None:
+        kernel_events[0].record()
     graph.owned_scatter("jaccard+adamic_adar", node_range[0], node_range[1], peer_adamic_adar.slices_dev_ptr, peer_adamic_adar.world,
                         peer_adamic_adar.length, node_weights, jaccard_slices_dev_ptr=peer_jaccard.slices_dev_ptr)
+    if kernel_events is not None:
+        kernel_events[1].record()
     peer_jaccard.barrier()
     peer_adamic_adar.barrier()
     return peer_jaccard.tensor, peer_adamic_adar.tensor

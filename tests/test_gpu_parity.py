@@ -907,6 +907,33 @@ def test_gcn_norm_edge_cases():
         gcn_norm(torch.tensor([[0, 5], [1, 0]]), None, 3, device=DEV)
     with pytest.raises(ValueError):
         gcn_norm(torch.tensor([[0, 1], [1, 0]]), torch.ones(3), 2, device=DEV)
+    # forward only: a tensor that wants gradients is refused instead of silently losing them
+    prop = GcnPropagation(torch.tensor([[0, 1], [1, 0]]), None, 2, device=DEV)
+    xg = torch.ones((2, 4), device=DEV, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        prop(xg)
+    with torch.no_grad():
+        assert prop(xg).shape == (2, 4)
+
+
+def test_degree_aware_zero_budget_quirk_and_prefetched_host_scores():
+    """min_edges_per_node = 0: the reference's `argsort(...)[-0:]` guarantees EVERY incident edge, so the full graph comes back
+    (core.py:432-434); negative budgets are refused. `prefetch_scores(to_host=True)` reads the vectors back behind their
+    kernels: same bytes as the blocking path, in any order of consumption."""
+    ei, x, n = named_graph("roman_empire")
+    sp = make_sparsifier(ei, n, x)
+    out, mask = sp.sparsify_degree_aware("jaccard", 0.3, min_edges_per_node=0, return_mask=True)
+    assert bool(mask.all()) and out.edge_index.size(1) == ei.shape[1]
+    with pytest.raises(ValueError):
+        sp.sparsify_degree_aware("jaccard", 0.3, min_edges_per_node=-1)
+    host = gsr_b200.Data(edge_index=torch.from_numpy(ei).pin_memory(), x=torch.from_numpy(x).pin_memory(), num_nodes=n)
+    pre = gsr_b200.GraphSparsifier(host.to(DEV, non_blocking=True), DEV)
+    pre.prefetch_scores(["jaccard", "adamic_adar", "feature_cosine"], to_host=True)
+    for m in ("feature_cosine", "jaccard", "adamic_adar"):
+        assert bits_equal(pre.compute_scores(m), sp.compute_scores(m)), m
+    a, ma = pre.sparsify("adamic_adar", 0.6, return_mask=True)
+    b, mb = sp.sparsify("adamic_adar", 0.6, return_mask=True)
+    assert torch.equal(ma, mb) and torch.equal(a.edge_index.cpu(), b.edge_index.cpu())
 
 
 def test_async_upload_builds_the_graph_beside_the_feature_copy():
