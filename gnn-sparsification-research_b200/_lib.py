@@ -79,6 +79,7 @@ PROTOTYPES = {
     "gsp_approx_er_partial_philox": (_INT, [_P, C.c_uint64, _I32, _I32, _I32, _I32, _F64, _F64, _I64, _I64, _P, _P, _P]),
     "gsp_philox_projection": (_INT, [C.c_uint64, _I64, _I32, _I32, _I32, _P, _P]),
     "gsp_er_finalize": (_INT, [_P, _I64, _P]),
+    "gsp_laplacian_solve": (_INT, [_P, _P, _I32, _I32, _F64, _F64, _P, _P, _P]),
     "gsp_sssp_batch": (_INT, [_P, _P, _I64, _I32, _P, _I32, C.POINTER(C.c_int32), _P]),
     "gsp_sssp_sources": (_INT, [_P, _P, _P, _I32, _P, _I32, C.POINTER(C.c_int32), _P]),
     "gsp_select_begin": (_INT, [_P, _I64, _INT, _P]),

@@ -576,20 +576,25 @@ int ensure_und_id(Graph* g, void* stream) {
 
 using namespace gsp;
 
+// `d_rhs` / `d_solution` (both [n, k] row-major, optional): solve for an explicit right-hand side instead of the projected
+// incidence columns and hand the solution out instead of the per-edge resistance sums (gsp_laplacian_solve).
 static int approx_er_partial(const gsp_graph* gg, const Projection& pr, int32_t k, int32_t max_iters, double rtol, double reg,
-                             int64_t e_begin, int64_t e_end, double* d_partial, int32_t* d_iters, void* stream) {
+                             int64_t e_begin, int64_t e_end, double* d_partial, int32_t* d_iters, void* stream,
+                             const double* d_rhs = nullptr, double* d_solution = nullptr) {
     GSP_REQUIRE(gg != nullptr, "graph is NULL");
     Graph* g = const_cast<Graph*>(reinterpret_cast<const Graph*>(gg));
     GSP_REQUIRE(e_begin >= 0 && e_begin <= e_end && e_end <= g->nnz, "edge range outside [0, nnz]");
     GSP_REQUIRE(k >= 1 && max_iters >= 0, "bad k / max_iters");
-    GSP_REQUIRE(e_end == e_begin || d_partial, "NULL argument");
+    GSP_REQUIRE(e_end == e_begin || d_partial || d_solution, "NULL argument");
     if (!g->symmetric) {
         set_error("approximate effective resistance needs a symmetric adjacency pattern (reference metrics.py:208-209)");
         return GSP_ERR_UNSUPPORTED;
     }
     cudaStream_t s = as_stream(stream);
     const int64_t n = g->n;
-    if (int rc = ensure_und_id(g, stream)) return rc;
+    if (!d_rhs) {
+        if (int rc = ensure_und_id(g, stream)) return rc;
+    }
     if (int rc = ensure_segments(g, s)) return rc;
     const int64_t extra_segments = g->num_seg_items - n;   // > 0 when some row is longer than kSeg
 
@@ -630,12 +635,16 @@ static int approx_er_partial(const gsp_graph* gg, const Projection& pr, int32_t 
     diag_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, g->indptr, g->indices, g->data, reg, diag.ptr);
     GSP_CHECK_LAUNCH();
     const SegItem* seg_items = reinterpret_cast<const SegItem*>(g->seg_items);
-    project_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->und_id, pr,
-                                               k, r.ptr, segpart.ptr);
-    GSP_CHECK_LAUNCH();
-    if (extra_segments > 0) {
-        project_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, k, r.ptr, segpart.ptr);
+    if (d_rhs) {
+        GSP_CUDA_TRY(cudaMemcpyAsync(r.ptr, d_rhs, vec * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else {
+        project_kernel<<<grid2d, kThreads, 0, s>>>(seg_items, g->num_seg_items, g->seg_incl, g->indptr, g->indices, g->und_id, pr,
+                                                   k, r.ptr, segpart.ptr);
         GSP_CHECK_LAUNCH();
+        if (extra_segments > 0) {
+            project_combine_kernel<<<grid2d, kThreads, 0, s>>>(n, g->seg_incl, g->indptr, k, r.ptr, segpart.ptr);
+            GSP_CHECK_LAUNCH();
+        }
     }
     init_kernel<<<grid2d, kThreads, 0, s>>>(n, k, r.ptr, x.ptr, partial.ptr);
     GSP_CHECK_LAUNCH();
@@ -679,7 +688,9 @@ static int approx_er_partial(const gsp_graph* gg, const Projection& pr, int32_t 
         update_kernel<<<grid2d, kThreads, 0, s>>>(n, k, p.ptr, q.ptr, x.ptr, r.ptr, cg, partial.ptr);
         GSP_CHECK_LAUNCH();
     }
-    if (e_end > e_begin) {
+    if (d_solution) {
+        GSP_CUDA_TRY(cudaMemcpyAsync(d_solution, x.ptr, vec * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else if (e_end > e_begin) {
         const int64_t edges = e_end - e_begin;
         resistance_kernel<<<grid_for(edges, kWarps, 16), kThreads, 0, s>>>(e_begin, e_end, g->rows, g->indices, x.ptr, k,
                                                                          d_partial);
@@ -702,6 +713,13 @@ GSP_API int gsp_approx_er_partial_philox(const gsp_graph* gg, uint64_t seed, int
     GSP_REQUIRE(col_begin >= 0 && k >= 1 && k_total >= col_begin + k, "bad column range");
     const Projection pr{nullptr, 0, seed, col_begin, 1.0 / sqrt((double)k_total)};
     return approx_er_partial(gg, pr, k, max_iters, rtol, reg, e_begin, e_end, d_partial, d_iters, stream);
+}
+
+GSP_API int gsp_laplacian_solve(const gsp_graph* gg, const double* d_rhs, int32_t k, int32_t max_iters, double rtol, double reg,
+                                double* d_x, int32_t* d_iters, void* stream) {
+    GSP_REQUIRE(d_rhs != nullptr && d_x != nullptr, "NULL argument");
+    const Projection none{nullptr, 0, 0, 0, 1.0};
+    return approx_er_partial(gg, none, k, max_iters, rtol, reg, 0, 0, nullptr, d_iters, stream, d_rhs, d_x);
 }
 
 GSP_API int gsp_philox_projection(uint64_t seed, int64_t m, int32_t col_begin, int32_t k, int32_t k_total, double* d_R,

@@ -278,6 +278,19 @@ class DeviceGraph:
                                                   ptr(r), self._stream()))
         return r
 
+    def laplacian_solve(self, rhs: torch.Tensor, max_iters=500, rtol=1e-6, reg=1e-6, return_iters=False):
+        """X = CG(D - A + reg*I, rhs) column by column (fp64 [n, k]; SciPy cg semantics per column; `gsp_laplacian_solve`)."""
+        if rhs.dim() != 2 or rhs.size(0) != self.num_nodes or rhs.dtype != torch.float64:
+            raise ValueError("rhs must be fp64 [num_nodes, k]")
+        rhs = rhs.to(self.device).contiguous()
+        k = rhs.size(1)
+        x = torch.empty_like(rhs)
+        iters = self._empty(k, torch.int32) if return_iters else None
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_laplacian_solve(self._handle, ptr(rhs), k, int(max_iters), float(rtol), float(reg), ptr(x), ptr(iters),
+                                                self._stream()))
+        return (x, iters) if return_iters else x
+
     def er_finalize(self, partial: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(self.device):
             check(self._lib.gsp_er_finalize(ptr(partial), partial.numel(), self._stream()))

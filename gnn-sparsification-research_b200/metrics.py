@@ -125,21 +125,46 @@ def calculate_approx_effective_resistance_scores(adj, epsilon: float = 0.3, seed
     return _approx_er_on_graph(g, epsilon, seed, max_cg_iters, cg_tol, k, projection).cpu().numpy()
 
 
-def _exact_er_on_graph(g: DeviceGraph) -> torch.Tensor:
-    """Exact effective resistance through a dense pseudo-inverse (reference metrics.py:158-175; O(n^3), small
-    graphs only). Library call (torch.linalg.pinv, fp64) — outside the hand-written hot path."""
+def _exact_er_on_graph(g: DeviceGraph, rtol: float = 1e-11, max_iters: int = 0) -> torch.Tensor:
+    """Exact effective resistance R(u,v) = L+[u,u] + L+[v,v] - 2 L+[u,v] (reference metrics.py:158-175, which forms the
+    dense pseudo-inverse of L + 1e-10 I: O(n^3)). Here only the columns of L+ that the edges need are computed, by the
+    batched Laplacian CG of the ApproxER path (`gsp_laplacian_solve`) with one right-hand side per node,
+    b_j = e_j - 1_C(j)/|C(j)| (the component's constant vector projected out, so the 1e10-sized null-space term of the
+    reference's regularised inverse — which cancels in R anyway — never enters the arithmetic). Small graphs only, like
+    the reference: n^2 fp64 per column block. Asymmetric patterns (outside the reference's contract) keep the dense path."""
     n = g.num_nodes
     if n > 20000:
-        raise ValueError("exact effective resistance is dense O(n^3); use approx_er for large graphs")
+        raise ValueError("exact effective resistance is O(n^2) memory and n solves; use approx_er for large graphs")
     indptr, indices, data, rows = g.export(with_data=True, with_rows=True)
     rows, cols = rows.long(), indices.long()
-    lap = torch.zeros((n, n), dtype=torch.float64, device=g.device)
-    lap.index_put_((rows, cols), -data, accumulate=True)
-    deg = torch.zeros(n, dtype=torch.float64, device=g.device).index_add_(0, rows, data)
-    lap += torch.diag(deg + 1e-10)
-    pinv = torch.linalg.pinv(lap, hermitian=g.symmetric)
-    r_eff = pinv[rows, rows] + pinv[cols, cols] - 2.0 * pinv[rows, cols]
-    return torch.clamp_min(r_eff, 1e-10)
+    if not g.symmetric:
+        lap = torch.zeros((n, n), dtype=torch.float64, device=g.device)
+        lap.index_put_((rows, cols), -data, accumulate=True)
+        deg = torch.zeros(n, dtype=torch.float64, device=g.device).index_add_(0, rows, data)
+        lap += torch.diag(deg + 1e-10)
+        pinv = torch.linalg.pinv(lap)
+        return torch.clamp_min(pinv[rows, rows] + pinv[cols, cols] - 2.0 * pinv[rows, cols], 1e-10)
+    from .topology import connected_components
+
+    label, _ = connected_components(g)
+    label = label.long()
+    size = torch.bincount(label, minlength=n).to(torch.float64)
+    inv_size = 1.0 / size[label]                                  # per node: 1 / |its component|
+    z_diag = torch.zeros(n, dtype=torch.float64, device=g.device)
+    z_edge = torch.zeros(g.nnz, dtype=torch.float64, device=g.device)
+    block = max(1, min(n, int(2e9 // (8 * max(n, 1)))))            # <= 2 GB per [n, block] fp64 vector (the solver keeps five)
+    iters_cap = max_iters if max_iters > 0 else max(2000, 8 * n)
+    for c0 in range(0, n, block):
+        c1 = min(n, c0 + block)
+        j = torch.arange(c0, c1, device=g.device)
+        rhs = -(label.unsqueeze(1) == label[j].unsqueeze(0)).to(torch.float64) * inv_size[j].unsqueeze(0)
+        rhs[j, j - c0] += 1.0
+        x = g.laplacian_solve(rhs, max_iters=iters_cap, rtol=rtol, reg=1e-10)
+        z_diag[j] = x[j, j - c0]
+        sel = (cols >= c0) & (cols < c1)
+        z_edge[sel] = x[rows[sel], cols[sel] - c0]
+        del rhs, x
+    return torch.clamp_min(z_diag[rows] + z_diag[cols] - 2.0 * z_edge, 1e-10)
 
 
 def calculate_effective_resistance_scores(adj) -> np.ndarray:

@@ -6,9 +6,9 @@ Same names, argument (a symmetric SciPy CSR adjacency), dictionary keys and conv
 loop counted once, NetworkX degrees (a loop counts twice), average local clustering coefficient, connected components and
 the share of the largest one, algebraic connectivity of the graph (of its largest component when disconnected). Triangles
 come from the intersection counts of the Jaccard pass (`gsp_node_triangles`), components from `gsp_connected_components`.
-The algebraic connectivity is a dense symmetric eigenproblem on the device (`torch.linalg.eigvalsh`) for components of up
-to `dense_limit` nodes — a convenience like the exact effective resistance, not a hand-written kernel; larger components
-report NaN (the reference's NetworkX solver is not practical there either).
+The algebraic connectivity of a component of up to `dense_limit` nodes is a dense symmetric eigenproblem on the device
+(`torch.linalg.eigvalsh`); larger components go through shift-and-invert Lanczos on the batched Laplacian CG of the
+ApproxER path (`_fiedler_shift_invert`), so there is no size beyond which the value is missing.
 """
 from __future__ import annotations
 
@@ -50,11 +50,49 @@ def connected_components(g: DeviceGraph):
     return label, int(rounds.value)
 
 
+def _fiedler_shift_invert(g: DeviceGraph, member: torch.Tensor, size: int, tol: float = 1e-9, max_steps: int = 60) -> float:
+    """Second smallest Laplacian eigenvalue of the component `member` (bool[n]) by shift-and-invert Lanczos: the operator
+    is (L + sigma I)^-1 restricted to the component and to the complement of its constant vector, applied with the batched
+    CG of the ApproxER path (`gsp_laplacian_solve`, one column); the wanted eigenvalue is the LARGEST of that operator, so a
+    few dozen Lanczos steps with full reorthogonalisation settle it where plain Lanczos on L would need thousands on
+    chain-like graphs. Weights = the matrix values, like nx.algebraic_connectivity (reference metrics.py:480-511)."""
+    dev = g.device
+    n = g.num_nodes
+    ones = member.to(torch.float64) / np.sqrt(size)
+    sigma = 1e-9 * max(float(g.max_degree), 1.0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    v = torch.randn(n, dtype=torch.float64, device=dev, generator=gen) * member
+    v -= torch.dot(ones, v) * ones
+    v /= torch.linalg.norm(v)
+    basis, alphas, betas = [v], [], []
+    lam = float("nan")
+    for step in range(max_steps):
+        w = g.laplacian_solve(basis[-1].unsqueeze(1), max_iters=200000, rtol=1e-12, reg=sigma).squeeze(1) * member
+        w -= torch.dot(ones, w) * ones
+        alpha = float(torch.dot(basis[-1], w))
+        alphas.append(alpha)
+        for _ in range(2):                                        # full reorthogonalisation, twice
+            q = torch.stack(basis, dim=1)
+            w -= q @ (q.T @ w)
+        beta = float(torch.linalg.norm(w))
+        t = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1) if betas else np.array([[alpha]])
+        theta, vecs = np.linalg.eigh(t)
+        new = 1.0 / theta[-1] - sigma
+        residual = abs(beta * vecs[-1, -1]) / abs(theta[-1])       # Ritz residual of the largest pair, relative
+        if residual < tol or beta < 1e-14 or (step > 0 and abs(new - lam) <= tol * abs(new) and residual < 1e-6):
+            return float(new)
+        lam = new
+        betas.append(beta)
+        basis.append(w / beta)
+    return float(lam)
+
+
 def _algebraic_connectivity(g: DeviceGraph, label: torch.Tensor, root: int, size: int, dense_limit: int) -> float:
     if size <= 1:
         return 0.0
     if size > dense_limit:
-        return float("nan")
+        return _fiedler_shift_invert(g, label == root, size)
     indptr, indices, data, rows = g.export(with_data=True, with_rows=True)
     nodes = torch.nonzero(label == root).flatten()
     local = torch.full((g.num_nodes,), -1, dtype=torch.int64, device=g.device)

@@ -200,6 +200,12 @@ int gsp_approx_er_partial_philox(const gsp_graph* g, uint64_t seed, int32_t col_
                                  double* d_partial, int32_t* d_iters, void* stream);
 int gsp_philox_projection(uint64_t seed, int64_t m, int32_t col_begin, int32_t k, int32_t k_total, double* d_R, void* stream);
 int gsp_er_finalize(double* d_score, int64_t count, void* stream);
+/* The batched solver on its own: X = CG(D - A + reg*I, RHS) for fp64 [n, k] row-major right-hand sides, same column-wise
+ * SciPy cg semantics, symmetric graphs. Used by the exact effective resistance (reference metrics.py:158-175: the columns
+ * of the Laplacian pseudo-inverse that the edges need, instead of a dense O(n^3) pinv) and by the algebraic connectivity
+ * of large components (metrics.py:480-511: shift-and-invert Lanczos). d_iters (optional) int32[k]. */
+int gsp_laplacian_solve(const gsp_graph* g, const double* d_rhs, int32_t k, int32_t max_iters, double rtol, double reg,
+                        double* d_x, int32_t* d_iters, void* stream);
 
 /* ---- metric backbone ---------------------------------------------------------------
  * Shortest-path lengths from the sources [src_begin, src_begin + src_count) to every node of a SYMMETRIC graph with

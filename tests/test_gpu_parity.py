@@ -311,6 +311,40 @@ def test_approx_er_products_shaped(regime):
         assert (a & b).sum() / k >= 0.999, (regime, r)
 
 
+def test_exact_effective_resistance_against_reference_goldens():
+    """`compute_scores("er")` — the columns of the Laplacian pseudo-inverse by batched CG solves instead of a dense pinv —
+    against what the live reference returned (tests/golden/exact_er.npz, oracle/make_exact_er_golden.py). The reference
+    inverts L + 1e-10 I densely, so its values carry the cancellation noise of a 1e10-sized null-space term (1e-6..6e-6
+    relative, stored per graph): the bar against it is 2e-5; against the regularisation-free pseudo-inverse it is 1e-8."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "exact_er.npz"))
+    for name in ("karate_unsorted", "triangle", "star_isolated", "two_triangles", "rmat_300", "chain_400"):
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        sp = make_sparsifier(g["edge_index"], int(g["num_nodes"]))
+        got = sp.compute_scores("effective_resistance")
+        assert float(gold[name + "__reference_noise"]) < 1e-5
+        np.testing.assert_allclose(got, gold[name], rtol=2e-5, err_msg=name)
+        np.testing.assert_allclose(got, gold[name + "__clean"], rtol=1e-8, err_msg=name + " (clean pinv)")
+
+
+def test_algebraic_connectivity_by_shift_invert_lanczos():
+    """Components beyond the dense eigen-solver's limit: shift-and-invert Lanczos on the batched Laplacian CG. Forced here
+    (dense_limit = 0) on graphs small enough for the goldens of the live reference (NetworkX tracemin_lu): 1e-6."""
+    import json
+
+    from gsr_b200.topology import compute_topology_metrics
+    from oracle.make_topology_golden import adjacency, graphs
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "topology_metrics.json")))
+    for name, ei, n in graphs():
+        if name not in ("karate_unsorted", "rmat_300", "chain_400", "rmat_2000", "chain_shortcuts_1500", "blocks_with_loops", "asymmetric_kept"):
+            continue
+        adj = adjacency(ei, n)
+        adj.data[:] = 1.0
+        got = compute_topology_metrics(adj, dense_limit=0)["algebraic_connectivity"]
+        want = gold[name]["algebraic_connectivity"]
+        assert abs(got - want) <= 1e-6 * max(1.0, want), (name, got, want)
+
+
 def test_approx_er_generated_projection_is_the_matrix_it_writes_out():
     """Throughput mode draws R[e, c] inside the projection kernel (Philox4x32-10 + Box-Muller, no [m, k] matrix in memory):
     the scores equal, bit for bit, those of the explicit-matrix entry point fed with `gsp_philox_projection`'s output;
