@@ -148,9 +148,8 @@ class GraphSparsifier:
             self._graph_ready = None
 
     def _join_graph(self) -> None:
-        """Only the graph build becomes a dependency of the caller's stream: feature-cosine scoring (which needs the
-        graph and the features, not the neighbourhood scores) then runs beside the neighbourhood pass still on the side
-        stream instead of behind it."""
+        """Only the graph build becomes a dependency of the caller's stream (work that needs the graph but not the
+        neighbourhood scores of a pass still running on the side stream)."""
         ready = getattr(self, "_graph_ready", None)
         if ready is not None:
             torch.cuda.current_stream(self._side.device).wait_event(ready)
@@ -257,14 +256,16 @@ class GraphSparsifier:
             else:
                 jac, aa = g.jaccard_adamic_adar(self._aa_node_weights())
             self._dev_scores["jaccard"], self._dev_scores["adamic_adar"] = jac, aa
-        fused_keys = [k for k in ("jaccard", "adamic_adar") if k in keys and k in self._dev_scores and self._side_pending]
-        for k in keys:      # everything else first: it runs (and is read back) beside the neighbourhood pass of the side stream
-            if k not in fused_keys:
-                self._device_scores(k)
-                if to_host:
-                    self._start_host_copies([k])
         if to_host:
-            self._start_host_copies(fused_keys)
+            self._start_host_copies([k for k in keys if k in self._dev_scores])    # the neighbourhood scores first
+        for k in keys:
+            if k not in self._dev_scores and k not in self._score_cache:
+                # everything else runs BEHIND the neighbourhood pass: beside it, feature-cosine stretched the pass from 184 to
+                # ~240 ms (two 768-thread hub CTAs fill an SM; the kernels time-slice at CTA granularity)
+                self._join_side()
+            self._device_scores(k)
+            if to_host:
+                self._start_host_copies([k])
 
     def _start_host_copies(self, keys) -> None:
         """Queue the device-to-host copy of the fp64 vectors the reference API returns on the host (page-locked buffers,
