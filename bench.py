@@ -364,6 +364,7 @@ def main() -> None:
     mask = torch.empty(local, dtype=torch.uint8, device=dev)
     ei_local = ei[:, e_lo:e_hi].contiguous() if world > 1 else ei
     kept_out = torch.empty((2, num_keep if world == 1 else local), dtype=torch.int64, device=dev)
+    sharded_select = engine.ShardedSelect(dev, group) if world > 1 else None
     phases = ([BOTH] if fused else ["jaccard", "adamic_adar"]) + ["feature_cosine"]     # scoring launches of one step
 
     def new_events():
@@ -419,9 +420,8 @@ def main() -> None:
             ev[m][1].record()
             for s_loc in outs:                     # every method: top-50 % select + mask + compaction of its own scores
                 ev_sel[sel][0].record()
-                if world > 1:
-                    engine.select_mask_sharded(s_loc, num_keep, False, group, out=mask)
-                    engine.compact_edges(ei_local, mask, kept_out.size(1), out=kept_out)   # true count stays on the device
+                if world > 1:    # distributed boundary search + fused mask / compaction; the kept count stays on the device
+                    sharded_select(s_loc, num_keep, False, ei_local, mask=mask, out=kept_out)
                 else:
                     engine.select_compact(s_loc, num_keep, False, ei_local, mask=mask, out=kept_out)
                 ev_sel[sel][1].record()

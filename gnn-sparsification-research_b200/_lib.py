@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libgsp.so")
 SELECT_BINS = 2048
 SELECT_PASSES = 6
 SELECT_STATE_BYTES = 16384
+SELECT_SLOT_WORDS = 2050
+SELECT_SCRATCH_BYTES = 18944
 
 
 class GspError(RuntimeError):
@@ -89,6 +91,10 @@ PROTOTYPES = {
     "gsp_select_write_mask": (_INT, [_P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
     "gsp_select_mask": (_INT, [_P, _I64, _I64, _INT, _P, _INT, _P, _P]),
     "gsp_select_compact": (_INT, [_P, _I64, _I64, _INT, _P, _I64, _P, _P, _I64, _P, _INT, _P, _P]),
+    "gsp_select_histogram_slot": (_INT, [_P, _I64, _P, _INT, _P, _P]),
+    "gsp_select_pick_slots": (_INT, [_P, _P, _I32, _INT, _P]),
+    "gsp_select_tally": (_INT, [_P, _I64, _P, _P, _P, _P]),
+    "gsp_select_emit": (_INT, [_P, _I64, _P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _INT, _P, _P]),
     "gsp_degree_aware_guarantee": (_INT, [_P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "gsp_compact_edges": (_INT, [_P, _I64, _I64, _P, _P, _INT, _P, _I64, _P, _P, _P]),
 }

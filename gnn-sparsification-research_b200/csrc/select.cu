@@ -18,6 +18,7 @@ constexpr int kThreads = 256;
 constexpr int kBins = GSP_SELECT_BINS;
 constexpr int kPasses = GSP_SELECT_PASSES;
 constexpr int kMaxBlocks = 1184;  // 148 SMs x 8 resident CTAs
+constexpr int kSlotWords = kBins + 2;   // sharded select: histogram + (~min, max) of the live keys, one slot per rank
 static_assert(kBins == 2048, "pass layout assumes 11-bit digits");
 
 __host__ __device__ __forceinline__ int pass_shift(int p) { return p < 5 ? 53 - 11 * p : 0; }
@@ -81,14 +82,15 @@ __device__ __forceinline__ void tally_digit(unsigned int* sh, bool live, unsigne
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
 histogram_kernel(const double* __restrict__ scores, int64_t count, const uint8_t* __restrict__ exclude,
-                 SelectState* __restrict__ st, int pass, unsigned long long* __restrict__ hist) {
+                 SelectState* __restrict__ st, int pass, unsigned long long* __restrict__ hist,
+                 unsigned long long* __restrict__ ext) {
     if (st->resolved) return;   // the boundary key is known: nothing left to histogram
     __shared__ unsigned int sh[kBins];
     for (int i = threadIdx.x; i < kBins; i += kThreads) sh[i] = 0;
     __syncthreads();
     const int shift = pass_shift(pass), bits = pass_bits(pass);
     const int keep_lowest = st->keep_lowest;
-    const bool extrema = st->local_only != 0;
+    const bool extrema = st->local_only != 0 || ext != nullptr;
     const uint64_t prefix = st->prefix;
     const int hi_shift = shift + bits;  // bits above the current digit must match the prefix
     const unsigned int digit_mask = (1u << bits) - 1u;
@@ -141,18 +143,35 @@ histogram_kernel(const double* __restrict__ scores, int64_t count, const uint8_t
             kmax = b > kmax ? b : kmax;
         }
         if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
-            atomicMin(&st->live_min, kmin);
-            atomicMax(&st->live_max, kmax);
+            if (ext) {   // sharded caller: the slot travels with the histogram (zero-initialised, so the minimum is stored inverted)
+                atomicMax(&ext[0], ~kmin);
+                atomicMax(&ext[1], kmax);
+            } else {
+                atomicMin(&st->live_min, kmin);
+                atomicMax(&st->live_max, kmax);
+            }
         }
     }
 }
 
 // One warp: find the bucket holding the `remaining`-th smallest live key and descend into it.
-__global__ void pick_kernel(SelectState* st, const unsigned long long* __restrict__ hist, int pass) {
+// `slots` > 0: `hist` holds one [kBins histogram | ~min live key | max live key] slot per rank (all-gathered), summed here.
+__global__ void pick_kernel(SelectState* st, const unsigned long long* __restrict__ hist, int pass, int slots) {
     if (st->empty || st->resolved) return;
     const int lane = threadIdx.x;
-    if (st->local_only) {
-        const unsigned long long lo = st->live_min, hi = st->live_max;
+    const int nsum = slots > 0 ? slots : 1;
+    const int stride = slots > 0 ? kSlotWords : 0;
+    if (st->local_only || slots > 0) {
+        unsigned long long lo = st->live_min, hi = st->live_max;
+        if (slots > 0) {
+            lo = ~0ull;
+            hi = 0ull;
+            for (int r = 0; r < slots; ++r) {
+                const unsigned long long a = ~hist[(size_t)r * kSlotWords + kBins], b = hist[(size_t)r * kSlotWords + kBins + 1];
+                lo = a < lo ? a : lo;
+                hi = b > hi ? b : hi;
+            }
+        }
         __syncwarp();
         if (lane == 0) {
             if (pass == 0) st->best_key = lo;
@@ -170,7 +189,8 @@ __global__ void pick_kernel(SelectState* st, const unsigned long long* __restric
     const int bits = pass_bits(pass), shift = pass_shift(pass);
     const int nbins = 1 << bits, per = nbins / 32;
     unsigned long long local = 0;
-    for (int i = 0; i < per; ++i) local += hist[lane * per + i];
+    for (int r = 0; r < nsum; ++r)
+        for (int i = 0; i < per; ++i) local += hist[(size_t)r * stride + lane * per + i];
     unsigned long long incl = local;
     for (int o = 1; o < 32; o <<= 1) {
         unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -185,7 +205,8 @@ __global__ void pick_kernel(SelectState* st, const unsigned long long* __restric
     if (mine) {
         unsigned long long run = excl;
         for (int i = 0; i < per; ++i) {
-            unsigned long long h = hist[lane * per + i];
+            unsigned long long h = 0;
+            for (int r = 0; r < nsum; ++r) h += hist[(size_t)r * stride + lane * per + i];
             if (want <= run + h) {
                 st->prefix |= (uint64_t)(lane * per + i) << shift;
                 st->remaining = (int64_t)(want - run);
@@ -476,7 +497,8 @@ __device__ __forceinline__ void load4(const double* __restrict__ scores, int64_t
 }
 
 __global__ void __launch_bounds__(kThreads)
-fused_tally_kernel(const double* __restrict__ scores, int64_t count, const SelectState* __restrict__ st, FusedScratch* fs) {
+fused_tally_kernel(const double* __restrict__ scores, int64_t count, const SelectState* __restrict__ st, FusedScratch* fs,
+                   unsigned long long* __restrict__ totals) {
     __shared__ unsigned long long sh[2];
     if (threadIdx.x < 2) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -515,6 +537,10 @@ fused_tally_kernel(const double* __restrict__ scores, int64_t count, const Selec
     if (threadIdx.x == 0) {
         fs->block_below[blockIdx.x] = (long long)sh[0];
         fs->block_ties[blockIdx.x] = (long long)sh[1];
+        if (totals) {   // sharded caller: this rank's (below, ties), all-gathered before the emit
+            if (sh[0]) atomicAdd(&totals[0], sh[0]);
+            if (sh[1]) atomicAdd(&totals[1], sh[1]);
+        }
     }
 }
 
@@ -522,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 5)
 fused_emit_kernel(const double* __restrict__ scores, int64_t count, const SelectState* __restrict__ st,
                   const FusedScratch* __restrict__ fs, const int64_t* __restrict__ ei, int64_t ld, int invert,
                   uint8_t* __restrict__ mask, int64_t* __restrict__ out_ei, int64_t out_ld, float* __restrict__ out_w,
-                  int64_t* __restrict__ num_kept) {
+                  int64_t* __restrict__ num_kept, const long long* __restrict__ rank_totals, int rank, int nranks) {
     __shared__ long long red[3][kThreads / 32];
     __shared__ unsigned int warp_tot[2][kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -549,6 +575,15 @@ fused_emit_kernel(const double* __restrict__ scores, int64_t count, const Select
     __syncthreads();
     below_before = ties_before = ties_total = 0;
     for (int w = 0; w < kThreads / 32; ++w) { below_before += red[0][w]; ties_before += red[1][w]; ties_total += red[2][w]; }
+    long long ties_lower_ranks = 0;   // sharded: tie ranks are global (rank order == position order)
+    if (rank_totals) {
+        ties_total = 0;
+        for (int r = 0; r < nranks; ++r) {
+            const long long tr = rank_totals[2 * r + 1];
+            ties_total += tr;
+            if (r < rank) ties_lower_ranks += tr;
+        }
+    }
     // window of tie ranks (position order) that are kept: the highest ones for top-k, the lowest ones for keep_lowest
     const long long win_lo = keep_lowest ? 0 : max(ties_total - need, 0ll);
     const long long win_hi = keep_lowest ? min(need, ties_total) : ties_total;
@@ -564,7 +599,8 @@ fused_emit_kernel(const double* __restrict__ scores, int64_t count, const Select
     int64_t chunk = (count + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + kTile - 1) / kTile * kTile;
     const int64_t lo = blockIdx.x * chunk, hi = min(lo + chunk, count);
-    long long tie_base = ties_before, kept_base = below_before + kept_ties_before(ties_before);
+    long long tie_base = ties_lower_ranks + ties_before;
+    long long kept_base = below_before + (kept_ties_before(tie_base) - kept_ties_before(ties_lower_ranks));
     int buf = 0;
     for (int64_t base = lo; base < hi; base += kTile, buf ^= 1) {
         const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
@@ -686,10 +722,10 @@ GSP_API int gsp_select_histogram(const double* d_scores, int64_t count, const ui
     SelectState* st = reinterpret_cast<SelectState*>(const_cast<void*>(d_state));
     if ((reinterpret_cast<uintptr_t>(d_scores) & 15) == 0)
         histogram_kernel<true><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, d_exclude, st, pass,
-                                                                                   reinterpret_cast<unsigned long long*>(d_hist));
+                                                                                   reinterpret_cast<unsigned long long*>(d_hist), nullptr);
     else
         histogram_kernel<false><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, d_exclude, st, pass,
-                                                                                    reinterpret_cast<unsigned long long*>(d_hist));
+                                                                                    reinterpret_cast<unsigned long long*>(d_hist), nullptr);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
@@ -698,7 +734,7 @@ GSP_API int gsp_select_pick(void* d_state, const uint64_t* d_hist, int pass, voi
     GSP_REQUIRE(d_state && d_hist, "NULL argument");
     GSP_REQUIRE(pass >= 0 && pass < kPasses, "pass out of range");
     pick_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state),
-                                                 reinterpret_cast<const unsigned long long*>(d_hist), pass);
+                                                 reinterpret_cast<const unsigned long long*>(d_hist), pass, 0);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }
@@ -767,10 +803,79 @@ GSP_API int gsp_select_compact(const double* d_scores, int64_t count, int64_t nu
     SelectState* st = reinterpret_cast<SelectState*>(state.ptr);
     if (int rc = select_boundary_local(d_scores, count, nullptr, num_keep, keep_lowest, st, hist.ptr, stream)) return rc;
     const int blocks = blocks_for(count);
-    fused_tally_kernel<<<blocks, kThreads, 0, s>>>(d_scores, count, st, fs.ptr);
+    fused_tally_kernel<<<blocks, kThreads, 0, s>>>(d_scores, count, st, fs.ptr, nullptr);
     GSP_CHECK_LAUNCH();
     fused_emit_kernel<<<blocks, kThreads, 0, s>>>(d_scores, count, st, fs.ptr, d_edge_index, ld, invert_weights, d_mask,
-                                                  d_out_edge_index, out_ld, d_out_weight, d_num_kept);
+                                                  d_out_edge_index, out_ld, d_out_weight, d_num_kept, nullptr, 0, 1);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+// ---- sharded select + compaction (one rank's slice; the caller all-gathers the slots and the totals) ------------------
+static_assert(kSlotWords == GSP_SELECT_SLOT_WORDS, "slot layout");
+static_assert(sizeof(FusedScratch) <= GSP_SELECT_SCRATCH_BYTES, "GSP_SELECT_SCRATCH_BYTES too small");
+
+GSP_API int gsp_select_histogram_slot(const double* d_scores, int64_t count, const void* d_state, int pass, uint64_t* d_slot,
+                                      void* stream) {
+    GSP_REQUIRE(d_state && d_slot, "NULL argument");
+    GSP_REQUIRE(count >= 0 && (count == 0 || d_scores), "bad scores");
+    GSP_REQUIRE(pass >= 0 && pass < kPasses, "pass out of range");
+    cudaStream_t s = as_stream(stream);
+    GSP_CUDA_TRY(cudaMemsetAsync(d_slot, 0, kSlotWords * sizeof(uint64_t), s));
+    if (count == 0) return GSP_OK;
+    SelectState* st = reinterpret_cast<SelectState*>(const_cast<void*>(d_state));
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(d_slot);
+    if ((reinterpret_cast<uintptr_t>(d_scores) & 15) == 0)
+        histogram_kernel<true><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, nullptr, st, pass, slot,
+                                                                                   slot + kBins);
+    else
+        histogram_kernel<false><<<grid_for(count, 8 * kThreads, 8), kThreads, 0, s>>>(d_scores, count, nullptr, st, pass, slot,
+                                                                                    slot + kBins);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_pick_slots(void* d_state, const uint64_t* d_slots, int32_t nranks, int pass, void* stream) {
+    GSP_REQUIRE(d_state && d_slots, "NULL argument");
+    GSP_REQUIRE(nranks >= 1, "nranks must be >= 1");
+    GSP_REQUIRE(pass >= 0 && pass < kPasses, "pass out of range");
+    pick_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<SelectState*>(d_state),
+                                                 reinterpret_cast<const unsigned long long*>(d_slots), pass, nranks);
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_tally(const double* d_scores, int64_t count, const void* d_state, void* d_scratch, int64_t* d_totals,
+                             void* stream) {
+    GSP_REQUIRE(d_state && d_scratch && d_totals, "NULL argument");
+    GSP_REQUIRE(count >= 0 && (count == 0 || d_scores), "bad scores");
+    cudaStream_t s = as_stream(stream);
+    GSP_CUDA_TRY(cudaMemsetAsync(d_totals, 0, 2 * sizeof(int64_t), s));
+    if (count == 0) return GSP_OK;
+    fused_tally_kernel<<<blocks_for(count), kThreads, 0, s>>>(d_scores, count, reinterpret_cast<const SelectState*>(d_state),
+                                                              reinterpret_cast<FusedScratch*>(d_scratch),
+                                                              reinterpret_cast<unsigned long long*>(d_totals));
+    GSP_CHECK_LAUNCH();
+    return GSP_OK;
+}
+
+GSP_API int gsp_select_emit(const double* d_scores, int64_t count, const void* d_state, const void* d_scratch,
+                            const int64_t* d_rank_totals, int32_t rank, int32_t nranks, const int64_t* d_edge_index, int64_t ld,
+                            uint8_t* d_mask, int64_t* d_out_edge_index, int64_t out_ld, float* d_out_weight, int invert_weights,
+                            int64_t* d_num_kept, void* stream) {
+    GSP_REQUIRE(count >= 0 && ld >= count && out_ld >= 0, "bad sizes");
+    GSP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+    cudaStream_t s = as_stream(stream);
+    if (count == 0) {
+        if (d_num_kept) GSP_CUDA_TRY(cudaMemsetAsync(d_num_kept, 0, sizeof(int64_t), s));
+        return GSP_OK;
+    }
+    GSP_REQUIRE(d_scores && d_state && d_scratch && d_rank_totals && d_edge_index, "NULL argument");
+    GSP_REQUIRE(out_ld == 0 || d_out_edge_index, "d_out_edge_index is NULL");
+    fused_emit_kernel<<<blocks_for(count), kThreads, 0, s>>>(
+        d_scores, count, reinterpret_cast<const SelectState*>(d_state), reinterpret_cast<const FusedScratch*>(d_scratch),
+        d_edge_index, ld, invert_weights, d_mask, d_out_edge_index, out_ld, d_out_weight, d_num_kept,
+        reinterpret_cast<const long long*>(d_rank_totals), rank, nranks);
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }

@@ -344,6 +344,54 @@ def select_compact(scores: torch.Tensor, num_keep: int, keep_lowest: bool, edge_
     return out, w, count
 
 
+class ShardedSelect:
+    """Reusable buffers + the call sequence of the sharded select + compaction (`gsp_select_histogram_slot` ...
+    `gsp_select_emit`, include/gsp.h): per method two kinds of collectives — an all-gather of one 16 KB slot per radix pass
+    and one of (below, ties) per rank — and no host synchronisation."""
+
+    def __init__(self, device, group):
+        import torch.distributed as dist
+
+        self.dev, self.group = device, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.state = torch.empty(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(_lib.SELECT_SCRATCH_BYTES, dtype=torch.uint8, device=device)
+        self.slot = torch.empty(_lib.SELECT_SLOT_WORDS, dtype=torch.int64, device=device)
+        self.slots = torch.empty(self.world * _lib.SELECT_SLOT_WORDS, dtype=torch.int64, device=device)
+        self.totals = torch.empty(2, dtype=torch.int64, device=device)
+        self.rank_totals = torch.empty(2 * self.world, dtype=torch.int64, device=device)
+
+    def __call__(self, scores: torch.Tensor, num_keep: int, keep_lowest: bool, edge_index_local: torch.Tensor,
+                 mask: Optional[torch.Tensor] = None, with_weights: bool = False, invert_weights: bool = False,
+                 out: Optional[torch.Tensor] = None):
+        """`scores` / `edge_index_local` [2, n]: this rank's slice. Returns (mask slice, kept columns [2, capacity],
+        weights or None, device int64[1] count of kept columns on this rank)."""
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        n = scores.numel()
+        ei = edge_index_local if edge_index_local.is_contiguous() else edge_index_local.contiguous()
+        if mask is None:
+            mask = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        if out is None:
+            out = torch.empty((2, n), dtype=torch.int64, device=self.dev)
+        w = torch.empty(out.size(1), dtype=torch.float32, device=self.dev) if with_weights else None
+        count = torch.empty(1, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            s = stream_ptr(self.dev)
+            check(lib.gsp_select_begin(ptr(self.state), int(num_keep), int(bool(keep_lowest)), s))
+            for p in range(_lib.SELECT_PASSES):
+                check(lib.gsp_select_histogram_slot(ptr(scores), n, ptr(self.state), p, ptr(self.slot), s))
+                dist.all_gather_into_tensor(self.slots, self.slot, group=self.group)
+                check(lib.gsp_select_pick_slots(ptr(self.state), ptr(self.slots), self.world, p, s))
+            check(lib.gsp_select_tally(ptr(scores), n, ptr(self.state), ptr(self.scratch), ptr(self.totals), s))
+            dist.all_gather_into_tensor(self.rank_totals, self.totals, group=self.group)
+            check(lib.gsp_select_emit(ptr(scores), n, ptr(self.state), ptr(self.scratch), ptr(self.rank_totals), self.rank,
+                                      self.world, ptr(ei), ei.size(1), ptr(mask), ptr(out), out.size(1), ptr(w),
+                                      int(bool(invert_weights)), ptr(count), s))
+        return mask, out, w, count
+
+
 def degree_aware_guarantee(src: torch.Tensor, scores: torch.Tensor, num_nodes: int, min_per_node: int):
     """(uint8 mask of guaranteed edges, int64[1] count) — reference core.py:421-435."""
     lib = _lib.load()

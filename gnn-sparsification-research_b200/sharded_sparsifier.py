@@ -37,7 +37,7 @@ import torch.distributed as dist
 
 from . import sharding
 from .core import GraphSparsifier, _copy_stream, _to_host
-from .engine import DeviceGraph, compact_edges, select_mask_sharded
+from .engine import DeviceGraph, ShardedSelect
 
 _PEER_CACHE: Dict[tuple, Optional[sharding.PeerScoreSlices]] = {}
 
@@ -312,54 +312,44 @@ class ShardedGraphSparsifier(GraphSparsifier):
             take = g.nnz                                   # order[-0:] is the whole array (reference slicing quirk)
         else:
             take = min(num_keep, g.nnz)
-        mask = select_mask_sharded(scores, take, keep_lowest, self._group)
-        return self._finish_sharded(mask, return_mask)
+        sparse_data, _, mask = self._select_sharded(scores, take, keep_lowest, return_mask)
+        return (sparse_data, mask) if return_mask else sparse_data
 
-    def _finish_sharded(self, mask_local: torch.Tensor, return_mask: bool):
+    def _select_sharded(self, scores: torch.Tensor, take: int, keep_lowest: bool, want_mask: bool, with_weights: bool = False):
+        """Distributed boundary search + this rank's mask slice, kept columns (and "-W" weights) from one fused emit
+        (`engine.ShardedSelect`), then the ranks' kept lists concatenated in rank (= position) order."""
         lo, hi = self.local_range
-        kept_local, _, count = compact_edges(self._ei_dev[:, lo:hi], mask_local, hi - lo)
-        kept = sharding.all_gather_variable(kept_local[:, : int(count.item())], self._group, dim=1)
+        if getattr(self, "_select", None) is None:
+            self._select = ShardedSelect(scores.device, self._group)
+        mask_local, kept_local, w_local, count = self._select(scores, take, keep_lowest, self._ei_dev[:, lo:hi],
+                                                              with_weights=with_weights, invert_weights=keep_lowest)
+        k = int(count.item())
+        kept = sharding.all_gather_variable(kept_local[:, :k], self._group, dim=1)
+        w = sharding.all_gather_variable(w_local[:k], self._group, dim=0).to(self.device) if with_weights else None
         sparse_data = self.data.clone()
         sparse_data.edge_index = kept.to(self.device)
-        if not return_mask:
-            return sparse_data
+        if not want_mask:
+            return sparse_data, w, None
         if self.gather_outputs:
             mask_local = sharding.all_gather_variable(mask_local, self._group, dim=0)
-        return sparse_data, _to_host(mask_local.view(torch.bool))
+        return sparse_data, w, _to_host(mask_local.view(torch.bool))
 
     def sparsify_with_weights(self, metric: str, retention_ratio: float, keep_lowest: bool = False):
-        """Threshold sparsification + min-max "-W" weights (reference roman_empire_gpu.py:248-256): the mask comes from
-        the distributed select, min / max of the kept scores from two scalar all-reduces, the weights of this rank's kept
-        edges from the local compaction kernel's formula; returns (Data, full float32 weights on `device`, mask)."""
+        """Threshold sparsification + min-max "-W" weights (reference roman_empire_gpu.py:248-256): the extrema of the
+        kept scores are the boundary score and the globally best score, both known to every rank after the distributed
+        boundary search, so each rank's emit writes the weights of its own kept edges; returns (Data, full float32
+        weights on `device`, mask)."""
         if not self.sharded:
             return super().sparsify_with_weights(metric, retention_ratio, keep_lowest)
         self._check_ratio(retention_ratio)
         key = self._normalize_metric_name(metric)
         scores = self._slice_scores(key)
-        lo, hi = self.local_range
-        if retention_ratio == 1.0:
-            mask = torch.ones(hi - lo, dtype=torch.uint8, device=scores.device)
+        num_keep = int(self.num_edges * retention_ratio)
+        if retention_ratio == 1.0 or (num_keep == 0 and not keep_lowest):
+            take = self.graph.nnz                           # everything (ratio 1, or the reference's order[-0:] quirk)
         else:
-            num_keep = int(self.num_edges * retention_ratio)
-            take = self.graph.nnz if (num_keep == 0 and not keep_lowest) else min(num_keep, self.graph.nnz)
-            mask = select_mask_sharded(scores, take, keep_lowest, self._group)
-        kept_scores = scores[mask.bool()]
-        big = torch.finfo(torch.float64).max
-        ext = torch.stack([kept_scores.min() if kept_scores.numel() else scores.new_tensor(big),
-                           -(kept_scores.max() if kept_scores.numel() else scores.new_tensor(-big))])
-        dist.all_reduce(ext, op=dist.ReduceOp.MIN, group=self._group)     # min and -max in one collective
-        mn, mx = ext[0], -ext[1]
-        w = (kept_scores - mn) / (mx - mn + 1e-8)                        # fp64, the reference's NumPy expression
-        if keep_lowest:
-            w = 1.0 - w
-        w = sharding.all_gather_variable(w.to(torch.float32), self._group, dim=0)
-        kept_local, _, count = compact_edges(self._ei_dev[:, lo:hi], mask, hi - lo)
-        kept = sharding.all_gather_variable(kept_local[:, : int(count.item())], self._group, dim=1)
-        sparse_data = self.data.clone()
-        sparse_data.edge_index = kept.to(self.device)
-        if self.gather_outputs:
-            mask = sharding.all_gather_variable(mask, self._group, dim=0)
-        return sparse_data, w.to(self.device), _to_host(mask.view(torch.bool))
+            take = min(num_keep, self.graph.nnz)
+        return self._select_sharded(scores, take, keep_lowest, True, with_weights=True)
 
     # The replicated variants run the single-GPU code on the gathered score vector (`_device_scores`);
     # sparsify_degree_aware is inherited unchanged, the two that read host scores need the full vector.

@@ -268,6 +268,37 @@ int gsp_select_compact(const double* d_scores, int64_t count, int64_t num_keep, 
                        const int64_t* d_edge_index, int64_t ld, uint8_t* d_mask, int64_t* d_out_edge_index,
                        int64_t out_ld, float* d_out_weight, int invert_weights, int64_t* d_num_kept, void* stream);
 
+/* Sharded select + mask + compaction (+ "-W" weights): the multi-GPU form of gsp_select_compact, one rank's contiguous
+ * slice per call (rank order == canonical position order). Two small all-gathers replace the all-reduces of the phased
+ * protocol above and carry what ends the rounds early and what the weights need:
+ *
+ *   gsp_select_begin(state, num_keep, keep_lowest)
+ *   for pass in 0 .. GSP_SELECT_PASSES-1:
+ *       gsp_select_histogram_slot(scores, count, state, pass, slot)   slot = uint64[GSP_SELECT_SLOT_WORDS]:
+ *                                                                     histogram | ~min live key | max live key
+ *       [all-gather slot -> slots[nranks][GSP_SELECT_SLOT_WORDS]]
+ *       gsp_select_pick_slots(state, slots, nranks, pass)             sums the histograms; equal global extrema = the
+ *                                                                     boundary bucket is one tie class: later passes no-ops
+ *   gsp_select_tally(scores, count, state, scratch, totals)           totals = int64[2]: keys below the boundary, ties
+ *   [all-gather totals -> rank_totals[nranks][2]]
+ *   gsp_select_emit(scores, count, state, scratch, rank_totals, rank, nranks, edge_index, ld, mask, out, out_ld, w, ..)
+ *
+ * The emit writes this rank's mask slice and its kept columns in position order (the caller concatenates the ranks'
+ * lists); weights use the boundary score and the globally best score (pass 0 extrema) as the kept set's extrema, as
+ * gsp_select_compact does (reference core.py:232-245, roman_empire_gpu.py:248-256). `scratch` is
+ * GSP_SELECT_SCRATCH_BYTES of caller-owned device memory shared by tally and emit. */
+#define GSP_SELECT_SLOT_WORDS 2050
+#define GSP_SELECT_SCRATCH_BYTES 18944
+int gsp_select_histogram_slot(const double* d_scores, int64_t count, const void* d_state, int pass, uint64_t* d_slot,
+                              void* stream);
+int gsp_select_pick_slots(void* d_state, const uint64_t* d_slots, int32_t nranks, int pass, void* stream);
+int gsp_select_tally(const double* d_scores, int64_t count, const void* d_state, void* d_scratch, int64_t* d_totals,
+                     void* stream);
+int gsp_select_emit(const double* d_scores, int64_t count, const void* d_state, const void* d_scratch,
+                    const int64_t* d_rank_totals, int32_t rank, int32_t nranks, const int64_t* d_edge_index, int64_t ld,
+                    uint8_t* d_mask, int64_t* d_out_edge_index, int64_t out_ld, float* d_out_weight, int invert_weights,
+                    int64_t* d_num_kept, void* stream);
+
 /* Degree-aware guarantee phase — replaces reference core.py:421-435: for every source node
  * (d_src = edge_index[0], positional, any order) mark its top min(min_per_node, out-degree) edges by
  * (score, position). d_mask (uint8[count]) is overwritten; d_num_marked (int64[1]) = |G|. The fill phase

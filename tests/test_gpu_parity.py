@@ -552,6 +552,67 @@ def test_phased_select_with_emulated_shards():
             assert np.array_equal(got, want), (keep, kl)
 
 
+def test_sharded_select_compact_with_emulated_ranks():
+    """The sharded select + compaction C-ABI sequence (histogram_slot / pick_slots / tally / emit, include/gsp.h) on four
+    slices of one vector (one of them empty, one a single score) with the two all-gathers done by hand — the call sequence
+    `engine.ShardedSelect` issues per rank over NCCL. Mask, kept columns, count and "-W" weights must equal the single-GPU
+    `select_compact` (itself checked against the stable argsort and the reference's weight expression)."""
+    from gsr_b200 import _lib
+    from gsr_b200._lib import check, ptr, stream_ptr
+
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    n = 300000
+    dev = torch.device(DEV)
+    ei = torch.from_numpy(rng.integers(0, 1 << 40, (2, n))).to(dev)
+    cuts = [0, 70001, 70001, 70002, 211111, n]
+    world = len(cuts) - 1
+    jac_like = np.where(rng.random(n) < 0.55, 0.0, rng.random(n))          # a heavy tie class of exact zeros at the boundary
+    for scores in (rng.integers(0, 3, n).astype(np.float64), rng.standard_normal(n), jac_like, np.full(n, 0.25)):
+        t = torch.from_numpy(scores).to(dev)
+        order = np.argsort(scores, kind="stable")
+        for keep, kl in ((n // 2, False), (n // 2, True), (5, False), (n - 7, True), (n, False), (0, True)):
+            want_ei, want_w, want_cnt = engine.select_compact(t, keep, kl, ei, mask=(want_mask := torch.empty(n, dtype=torch.uint8, device=dev)),
+                                                              with_weights=True, invert_weights=kl)
+            ref_mask = np.zeros(n, bool)
+            ref_mask[order[:keep] if kl else order[n - keep:]] = True
+            assert np.array_equal(want_mask.cpu().numpy().astype(bool), ref_mask)
+            state = [torch.empty(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+            scratch = [torch.empty(_lib.SELECT_SCRATCH_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+            slots = torch.empty(world * _lib.SELECT_SLOT_WORDS, dtype=torch.int64, device=dev)
+            totals = torch.empty(2 * world, dtype=torch.int64, device=dev)
+            sl = [t[cuts[r]:cuts[r + 1]] for r in range(world)]
+            sp = stream_ptr(dev)
+            for r in range(world):
+                check(lib.gsp_select_begin(ptr(state[r]), keep, int(kl), sp))
+            for p in range(_lib.SELECT_PASSES):
+                for r in range(world):                                         # every rank's slot lands in the gathered buffer
+                    slot = slots[r * _lib.SELECT_SLOT_WORDS:(r + 1) * _lib.SELECT_SLOT_WORDS]
+                    check(lib.gsp_select_histogram_slot(ptr(sl[r]) if sl[r].numel() else None, sl[r].numel(), ptr(state[r]), p, ptr(slot), sp))
+                for r in range(world):
+                    check(lib.gsp_select_pick_slots(ptr(state[r]), ptr(slots), world, p, sp))
+            for r in range(world):
+                check(lib.gsp_select_tally(ptr(sl[r]) if sl[r].numel() else None, sl[r].numel(), ptr(state[r]), ptr(scratch[r]),
+                                           ptr(totals[2 * r:2 * r + 2]), sp))
+            masks, cols, ws = [], [], []
+            for r in range(world):
+                m = sl[r].numel()
+                e_loc = ei[:, cuts[r]:cuts[r + 1]].contiguous()
+                mask = torch.empty(m, dtype=torch.uint8, device=dev)
+                out = torch.empty((2, m), dtype=torch.int64, device=dev)
+                w = torch.empty(m, dtype=torch.float32, device=dev)
+                cnt = torch.full((1,), -1, dtype=torch.int64, device=dev)
+                check(lib.gsp_select_emit(ptr(sl[r]) if m else None, m, ptr(state[r]), ptr(scratch[r]), ptr(totals), r, world,
+                                          ptr(e_loc) if m else None, m, ptr(mask) if m else None, ptr(out) if m else None, m,
+                                          ptr(w) if m else None, int(kl), ptr(cnt), sp))
+                k = int(cnt.item())
+                masks.append(mask); cols.append(out[:, :k]); ws.append(w[:k])
+            total = int(want_cnt.item())
+            assert torch.equal(torch.cat(masks), want_mask), (keep, kl)
+            assert torch.equal(torch.cat(cols, dim=1), want_ei[:, :total]), (keep, kl)
+            assert torch.equal(torch.cat(ws).view(torch.int32), want_w[:total].view(torch.int32)), (keep, kl)
+
+
 def test_owner_sharded_scoring_sums_to_the_full_result():
     """Multi-GPU Jaccard/AA contract: pairs owned by disjoint node ranges, written into zero-filled full-length buffers,
     sum (what the NCCL reduce-scatter computes) to exactly the single-GPU score vector."""
