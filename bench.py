@@ -58,7 +58,11 @@ def measured_peak():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    Default: NVML in this process (the interface nvidia-smi itself reads), one light query every 10 ms from a thread set
+    up before the timed region starts — ~60 samples over a 2-GPU run where the CLI poll (`GSP_BENCH_CLOCKS=smi`,
+    `-lms 100`) returns 4-7. Neither perturbs the measurement (A/B: `profiles/tools/ab_clock_sampler.sh`)."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -68,8 +72,46 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.mode = os.environ.get("GSP_BENCH_CLOCKS", "nvml")
+
+    # -- NVML thread ---------------------------------------------------------------------------------
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((float(sm), int(reasons)))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
+        if self.mode == "nvml":
+            try:
+                import threading
+
+                nv, handle = self._nvml_handle()
+                self._nv, self._handle = nv, handle
+                self._max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+                self._stop = threading.Event()
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
+                self.mode = "smi"
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -79,8 +121,23 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Called when the timed region starts: earlier samples are dropped."""
+        self._mark = len(self.samples)
+
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            nv = self._nv
+            taken = self.samples[getattr(self, "_mark", 0):] or self.samples
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+            if taken:
+                out.update(sm_mhz=float(np.median([t[0] for t in taken])), sm_max_mhz=self._max, samples=len(taken),
+                           reasons=sorted({name for name, bit in names for t in taken if t[1] & bit}))
+            return out
         if self.proc is None:
             return out
         time.sleep(0.15)
@@ -110,7 +167,6 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
 def cpu_sample(total_steps: int) -> dict:
     """Bounded CPU sample of the workload: one step of the SciPy path costs ~9 s at R-MAT scale 15 and ~30 s at scale 16
     (SpGEMM fill-in grows faster than the edge count), so the scale follows the number of steps the caller will time."""
@@ -344,7 +400,11 @@ def main() -> None:
     slice_len, slices = sharding.equal_slices(e, world)     # every rank's contiguous slice of canonical positions
     e_lo, e_hi = slices[rank]
     local = e_hi - e_lo
-    node_range = sharding.owner_node_ranges(graph, world)[rank]
+    # owners dealt in cost order (GSP_BENCH_PARTITION=ranges: contiguous node ranges, for A/B)
+    if os.environ.get("GSP_BENCH_PARTITION", "deal") == "ranges":
+        node_range = sharding.owner_node_ranges(graph, world)[rank]
+    else:
+        node_range = sharding.install_owner_deal(graph, world, rank)
     fused = os.environ.get("GSP_BENCH_FUSED", "1") != "0"
     full_scratch = torch.empty(slice_len * world * (2 if fused else 1), dtype=torch.float64, device=dev) if world > 1 else None
     peer = peer_j = None
@@ -466,9 +526,11 @@ def main() -> None:
             single_ms[m] = a.elapsed_time(b)
     # the reported number — K steps back to back, no host sync inside, max over ranks
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     launches0 = lib.gsp_launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()

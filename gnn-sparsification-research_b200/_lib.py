@@ -62,6 +62,7 @@ PROTOTYPES = {
     "gsp_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P]),
     "gsp_jaccard_adamic_adar_owned": (_INT, [_P, _P, _I64, _I64, _P, _P, _P]),
     "gsp_owner_costs": (_INT, [_P, _P, _P]),
+    "gsp_graph_set_owner_deal": (_INT, [_P, _P, _I32, _P]),
     "gsp_jaccard_owned_scatter": (_INT, [_P, _I64, _I64, _P, _I32, _I64, _P]),
     "gsp_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _I32, _I64, _P]),
     "gsp_jaccard_adamic_adar_owned_scatter": (_INT, [_P, _P, _I64, _I64, _P, _P, _I32, _I64, _P]),

@@ -128,6 +128,10 @@ struct Graph {
     void* owned_items = nullptr;
     int64_t num_owned_items = 0, num_owned_hub_items = 0;
     int64_t owned_lo = -1, owned_hi = -1;
+    bool owned_dealt = false;
+    // dealt ownership (gsp_graph_set_owner_deal): owner o is evaluated by this process only when deal[o] == deal_rank
+    uint8_t* deal = nullptr;
+    int32_t deal_rank = -1;
 };
 
 // graph.cu: CUB inclusive scan wrapper shared by the lazily built side structures
@@ -135,13 +139,15 @@ int inclusive_sum_i64(const int64_t* in, int64_t* out, int64_t count, cudaStream
 int sort_pairs_u32_u64(const uint32_t* keys_in, uint32_t* keys_out, const uint64_t* vals_in, uint64_t* vals_out, int64_t count,
                        cudaStream_t s);
 // intersect_owner.cu: fast path for symmetric graphs (each undirected pair evaluated once at its owner)
+// `dealt`: honour the graph's owner deal (gsp_graph_set_owner_deal) — the *_owned entry points only
 int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
-                            double* score, cudaStream_t s);
+                            double* score, cudaStream_t s, bool dealt = false);
 int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
-                                const double* node_w, double* score, cudaStream_t s);
+                                const double* node_w, double* score, cudaStream_t s, bool dealt = false);
+int set_owner_deal(Graph* g, const uint8_t* d_owner_rank, int32_t rank, cudaStream_t s);
 int owner_costs(const Graph* g, double* cost, cudaStream_t s);
 int owner_intersect_both(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w,
-                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s);
+                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s, bool dealt = false);
 int owner_intersect_scatter(Graph* g, int mode, int64_t owner_lo, int64_t owner_hi, const double* node_w,
                             double* const* slices, int64_t slice_len, cudaStream_t s, double* const* slices2 = nullptr);
 

@@ -299,6 +299,7 @@ void free_graph(Graph* g) {
     device_free(g->rev_off);
     device_free(g->owner_items);
     device_free(g->owned_items);
+    device_free(g->deal);
     device_free(g->seg_items);
     device_free(g->seg_incl);
     delete g;

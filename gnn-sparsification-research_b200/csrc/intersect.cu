@@ -307,7 +307,7 @@ GSP_API int gsp_jaccard_owned(const gsp_graph* gg, int64_t node_begin, int64_t n
     const Graph* g = reinterpret_cast<const Graph*>(gg);
     if (int rc = check_owned(g, node_begin, node_end, d_score_full)) return rc;
     return owner_intersect_jaccard(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_inter_full, d_score_full,
-                                   as_stream(stream));
+                                   as_stream(stream), true);
 }
 
 GSP_API int gsp_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, int64_t node_begin, int64_t node_end,
@@ -321,7 +321,7 @@ GSP_API int gsp_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, i
         if (int rc = gsp_aa_node_weights(gg, w.ptr, stream)) return rc;
         d_node_w = w.ptr;
     }
-    return owner_intersect_adamic_adar(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, d_score_full, s);
+    return owner_intersect_adamic_adar(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, d_score_full, s, true);
 }
 
 GSP_API int gsp_jaccard_adamic_adar_owned(const gsp_graph* gg, const double* d_node_w, int64_t node_begin, int64_t node_end,
@@ -337,7 +337,14 @@ GSP_API int gsp_jaccard_adamic_adar_owned(const gsp_graph* gg, const double* d_n
         d_node_w = w.ptr;
     }
     return owner_intersect_both(const_cast<Graph*>(g), 0, g->nnz, node_begin, node_end, d_node_w, nullptr, d_jaccard_full,
-                                d_adamic_adar_full, s);
+                                d_adamic_adar_full, s, true);
+}
+
+GSP_API int gsp_graph_set_owner_deal(gsp_graph* gg, const uint8_t* d_owner_rank, int32_t rank, void* stream) {
+    Graph* g = reinterpret_cast<Graph*>(gg);
+    GSP_REQUIRE(g != nullptr, "graph is NULL");
+    GSP_REQUIRE(d_owner_rank == nullptr || (rank >= 0 && rank < 256), "rank must be in [0, 256)");
+    return set_owner_deal(g, d_owner_rank, rank, as_stream(stream));
 }
 
 // Peer-scatter variants: the scoring kernel itself delivers every score to the rank that owns its position

@@ -145,6 +145,8 @@ struct RangeInfo {
     int32_t row_lo, row_hi;   // rows holding the first / last position of the range
     bool full;
     int32_t owner_lo, owner_hi;  // only pairs owned by nodes in [owner_lo, owner_hi) are evaluated (owner sharding)
+    const uint8_t* deal;         // ... and, when set, only by owners dealt to this rank (deal[o] == deal_rank)
+    int32_t deal_rank;
     // peer scatter (multi-GPU): position p goes to slices[p / slice_len][p % slice_len]; the pointers may be peer
     // memory mapped over NVLink, so every score crosses the fabric exactly once, straight from the scoring kernel
     double* const* slices;
@@ -247,6 +249,7 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
             const int64_t a0 = __ldg(indptr + o), a1 = __ldg(indptr + o + 1);
             const int d_o = (int)(a1 - a0);
             if (d_o == 0 || d_o > kWarpOwnerMax) continue;
+            if (r.deal && r.deal[o] != r.deal_rank) continue;
             const bool row_in_range = r.full || (a0 < r.e_end && a1 > r.e_begin);
             // neighbours in registers: lane holds elements lane and lane + 32
             const int32_t nb0 = lane < d_o ? __ldg(indices + a0 + lane) : INT_MAX;
@@ -704,9 +707,12 @@ int ensure_items(Graph* g, cudaStream_t s) {
 }
 
 // ---- the items of one owner range (owner-sharded scoring) ---------------------------------------------------------
-__global__ void flag_owned_kernel(int64_t count, const OwnerItem* __restrict__ items, int32_t lo, int32_t hi, int64_t* __restrict__ flags) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        flags[i] = items[i].owner >= lo && items[i].owner < hi;
+__global__ void flag_owned_kernel(int64_t count, const OwnerItem* __restrict__ items, int32_t lo, int32_t hi,
+                                  const uint8_t* __restrict__ deal, int32_t deal_rank, int64_t* __restrict__ flags) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t o = items[i].owner;
+        flags[i] = o >= lo && o < hi && (!deal || deal[o] == deal_rank);
+    }
 }
 
 __global__ void gather_owned_kernel(int64_t count, const OwnerItem* __restrict__ items, const int64_t* __restrict__ flags,
@@ -716,9 +722,9 @@ __global__ void gather_owned_kernel(int64_t count, const OwnerItem* __restrict__
 }
 
 // Order-preserving filter of both item classes by owner range; cached for the last range used.
-int ensure_owned_items(Graph* g, int64_t owner_lo, int64_t owner_hi, cudaStream_t s) {
+int ensure_owned_items(Graph* g, int64_t owner_lo, int64_t owner_hi, bool dealt, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_items_mutex);
-    if (g->owned_items && g->owned_lo == owner_lo && g->owned_hi == owner_hi) return GSP_OK;
+    if (g->owned_items && g->owned_lo == owner_lo && g->owned_hi == owner_hi && g->owned_dealt == dealt) return GSP_OK;
     const int64_t total = g->num_owner_items + g->num_hub_items;
     if (g->owned_items) {     // kernels of an earlier call (any stream) may still read the list of the previous range
         GSP_CUDA_TRY(cudaDeviceSynchronize());
@@ -728,12 +734,14 @@ int ensure_owned_items(Graph* g, int64_t owner_lo, int64_t owner_hi, cudaStream_
     g->num_owned_items = g->num_owned_hub_items = 0;
     g->owned_lo = owner_lo;
     g->owned_hi = owner_hi;
+    g->owned_dealt = dealt;
     if (total == 0) return GSP_OK;
     const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
     Scratch<int64_t> flags, incl;
     GSP_CUDA_TRY(flags.alloc(total, s));
     GSP_CUDA_TRY(incl.alloc(total, s));
-    flag_owned_kernel<<<grid_for(total, 256), 256, 0, s>>>(total, items, (int32_t)owner_lo, (int32_t)owner_hi, flags.ptr);
+    flag_owned_kernel<<<grid_for(total, 256), 256, 0, s>>>(total, items, (int32_t)owner_lo, (int32_t)owner_hi,
+                                                           dealt ? g->deal : nullptr, g->deal_rank, flags.ptr);
     GSP_CHECK_LAUNCH();
     int64_t kept[2] = {0, 0};
     const int64_t counts[2] = {g->num_owner_items, g->num_hub_items};
@@ -797,12 +805,12 @@ int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, i
 
 template <int kMode, bool kScatter>
 int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w, int32_t* inter,
-           double* score, double* jaccard, cudaStream_t s, double* const* slices = nullptr, int64_t slice_len = 0,
+           double* score, double* jaccard, cudaStream_t s, bool dealt, double* const* slices = nullptr, int64_t slice_len = 0,
            double* const* slices2 = nullptr) {
     if (g->n == 0 || e_end == e_begin || owner_hi <= owner_lo) return GSP_OK;
     if (int rc = ensure_items(g, s)) return rc;
-    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi, slices, slice_len,
-                slices2};
+    RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi,
+                dealt ? g->deal : nullptr, g->deal_rank, slices, slice_len, slices2};
     if (!r.full) {
         Scratch<int32_t> rr;
         GSP_CUDA_TRY(rr.alloc(2, s));
@@ -826,8 +834,8 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     GSP_CUDA_TRY(cudaMemsetAsync(counters.ptr, 0, 3 * sizeof(unsigned long long), s));
     const OwnerItem* items = reinterpret_cast<const OwnerItem*>(g->owner_items);
     int64_t num_medium = g->num_owner_items, num_hub = g->num_hub_items;
-    if (owner_lo > 0 || owner_hi < g->n) {   // owner-sharded call: only this range's items are claimed
-        if (int rc = ensure_owned_items(g, owner_lo, owner_hi, s)) return rc;
+    if (owner_lo > 0 || owner_hi < g->n || r.deal) {   // owner-sharded call: only this rank's items are claimed
+        if (int rc = ensure_owned_items(g, owner_lo, owner_hi, r.deal != nullptr, s)) return rc;
         items = reinterpret_cast<const OwnerItem*>(g->owned_items);
         num_medium = g->num_owned_items;
         num_hub = g->num_owned_hub_items;
@@ -851,7 +859,11 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
 // Estimated work of every owner, in streamed-id equivalents: the ids of the owned neighbours' rows + a constant per
 // neighbour; the rows of an owner that needs several hash tiles are chopped into one piece per tile (a fixed cost per
 // piece) and their ids go through the costlier bounded rounds. Calibrated on 4 GPUs (R-MAT scale 24, fused pass): with
-// the plain id count the rank that holds the largest hubs ran 54.8 ms against 46.6-47.6 ms for the others.
+// the plain id count the rank that holds the largest hubs ran 54.8 ms against 46.6-47.6 ms for the others. The cost of a
+// piece (~80 bookkeeping instructions + a 64-id round that a short piece fills only in part, ncu source view) was then
+// fitted on the one owner no deal can spread: node 0 of R-MAT scale 24 (232 559 neighbours = 38 tiles, 8.8 M pieces of
+// ~14 ids) kept its rank ~2.3 ms behind the others at 2 and at 8 GPUs with 24 per piece.
+constexpr double kPieceCost = 110.0;
 __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                   double* __restrict__ cost) {
     const int lane = lane_id();
@@ -862,7 +874,7 @@ __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr,
         const int64_t a0 = indptr[o], a1 = indptr[o + 1];
         const int d_o = (int)(a1 - a0);
         const int tiles = d_o > hub_tile ? (d_o + hub_tile - 1) / hub_tile : 1;
-        const double per_id = tiles > 1 ? 1.3 : 1.0, per_row = 16.0 + (tiles > 1 ? 24.0 * tiles : 0.0);
+        const double per_id = tiles > 1 ? 1.3 : 1.0, per_row = 16.0 + (tiles > 1 ? kPieceCost * tiles : 0.0);
         double c = 0.0;
         for (int64_t p = a0 + lane; p < a1; p += kWarp) {
             const int32_t w = __ldg(indices + p);
@@ -874,28 +886,47 @@ __global__ void owner_cost_kernel(int64_t n, const int64_t* __restrict__ indptr,
     }
 }
 
+// Dealt ownership: a per-node rank byte replaces contiguous node ranges as the unit of owner sharding, so a caller can
+// hand every rank the same mix of hub / medium / small owners (e.g. owners sorted by cost and dealt in snake order).
+int set_owner_deal(Graph* g, const uint8_t* d_owner_rank, int32_t rank, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_items_mutex);
+    if (g->owned_items || g->deal) GSP_CUDA_TRY(cudaDeviceSynchronize());   // earlier kernels may still read the old lists
+    device_free(g->owned_items);
+    g->owned_items = nullptr;
+    g->num_owned_items = g->num_owned_hub_items = 0;
+    g->owned_lo = g->owned_hi = -1;
+    device_free(g->deal);
+    g->deal = nullptr;
+    g->deal_rank = -1;
+    if (d_owner_rank == nullptr || g->n == 0) return GSP_OK;
+    GSP_CUDA_TRY(device_alloc(&g->deal, (size_t)g->n, s));
+    GSP_CUDA_TRY(cudaMemcpyAsync(g->deal, d_owner_rank, (size_t)g->n, cudaMemcpyDeviceToDevice, s));
+    g->deal_rank = rank;
+    return GSP_OK;
+}
+
 int owner_intersect_jaccard(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, int32_t* inter,
-                            double* score, cudaStream_t s) {
-    return launch<0, false>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, nullptr, s);
+                            double* score, cudaStream_t s, bool dealt) {
+    return launch<0, false>(g, e_begin, e_end, owner_lo, owner_hi, nullptr, inter, score, nullptr, s, dealt);
 }
 
 int owner_intersect_adamic_adar(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi,
-                                const double* node_w, double* score, cudaStream_t s) {
-    return launch<1, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, nullptr, s);
+                                const double* node_w, double* score, cudaStream_t s, bool dealt) {
+    return launch<1, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, nullptr, score, nullptr, s, dealt);
 }
 
 // one streaming pass, both scores (and optionally the counts)
 int owner_intersect_both(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t owner_hi, const double* node_w,
-                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s) {
-    return launch<2, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, inter, adamic_adar, jaccard, s);
+                         int32_t* inter, double* jaccard, double* adamic_adar, cudaStream_t s, bool dealt) {
+    return launch<2, false>(g, e_begin, e_end, owner_lo, owner_hi, node_w, inter, adamic_adar, jaccard, s, dealt);
 }
 
 // mode 0: Jaccard into `slices`; 1: Adamic-Adar into `slices`; 2: Adamic-Adar into `slices`, Jaccard into `slices2`
 int owner_intersect_scatter(Graph* g, int mode, int64_t owner_lo, int64_t owner_hi, const double* node_w,
                             double* const* slices, int64_t slice_len, cudaStream_t s, double* const* slices2) {
-    if (mode == 0) return launch<0, true>(g, 0, g->nnz, owner_lo, owner_hi, nullptr, nullptr, nullptr, nullptr, s, slices, slice_len);
-    if (mode == 1) return launch<1, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, slices, slice_len);
-    return launch<2, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, slices, slice_len, slices2);
+    if (mode == 0) return launch<0, true>(g, 0, g->nnz, owner_lo, owner_hi, nullptr, nullptr, nullptr, nullptr, s, true, slices, slice_len);
+    if (mode == 1) return launch<1, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, true, slices, slice_len);
+    return launch<2, true>(g, 0, g->nnz, owner_lo, owner_hi, node_w, nullptr, nullptr, nullptr, s, true, slices, slice_len, slices2);
 }
 
 int owner_costs(const Graph* g, double* cost, cudaStream_t s) {

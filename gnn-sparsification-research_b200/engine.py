@@ -162,6 +162,16 @@ class DeviceGraph:
             check(self._lib.gsp_owner_costs(self._handle, ptr(cost), self._stream()))
         return cost
 
+    def set_owner_deal(self, owner_rank: Optional[torch.Tensor], rank: int = 0) -> None:
+        """Dealt ownership (`gsp_graph_set_owner_deal`): from now on the `*_owned*` calls of this handle evaluate only
+        owners o with `owner_rank[o] == rank` (uint8[num_nodes], copied); None clears the deal."""
+        if owner_rank is not None:
+            owner_rank = owner_rank.to(device=self.device, dtype=torch.uint8).contiguous()
+            if owner_rank.numel() != self.num_nodes:
+                raise ValueError("owner_rank must have num_nodes entries")
+        with torch.cuda.device(self.device):
+            check(self._lib.gsp_graph_set_owner_deal(self._handle, ptr(owner_rank), int(rank), self._stream()))
+
     def jaccard_owned(self, node_begin: int, node_end: int, out: torch.Tensor, counts: Optional[torch.Tensor] = None):
         """Scores of the pairs owned by nodes [node_begin, node_end) into the full-length (>= nnz) buffer `out`."""
         with torch.cuda.device(self.device):

@@ -158,7 +158,7 @@ class ShardedGraphSparsifier(GraphSparsifier):
 
     def _owner_range(self) -> Tuple[int, int]:
         if self._node_range is None:
-            self._node_range = sharding.owner_node_ranges(self.graph, self._world)[self._rank]
+            self._node_range = sharding.install_owner_deal(self.graph, self._world, self._rank)
         return self._node_range
 
     def _local(self, t: torch.Tensor) -> torch.Tensor:

@@ -69,6 +69,44 @@ def owner_node_ranges(graph, world: int) -> List[Tuple[int, int]]:
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+def owner_deal(costs: torch.Tensor, world: int, head: int = 4096) -> torch.Tensor:
+    """uint8[n] rank of every owner. Owners are sorted by estimated work (descending, stable); the `head` heaviest are
+    placed one by one on the least-loaded rank (longest-processing-time greedy, on the host: an outlier such as node 0 of
+    R-MAT scale 24, 3x the work of the runner-up, is compensated by the owners that follow it), the rest are dealt in snake
+    order (0 .. N-1, N-1 .. 0, ...). Every rank receives the same mix of hub, medium and small owners, so whatever the cost
+    estimate gets wrong about a class is spread evenly instead of landing on the rank whose node range holds the hubs
+    (contiguous ranges: 28.3 ms on rank 0 against 23.9-25.6 ms on the other seven, R-MAT scale 24)."""
+    import heapq
+
+    n = costs.numel()
+    order = torch.argsort(costs, descending=True, stable=True)
+    i = torch.arange(n, device=costs.device) % (2 * world)
+    dealt = torch.where(i < world, i, 2 * world - 1 - i).to(torch.uint8)
+    head = min(head - head % (2 * world), n - n % (2 * world))      # whole snake cycles, so the tail starts at rank 0
+    if head > 0:
+        top = costs[order[:head]].cpu().tolist()
+        loads = [(0.0, r) for r in range(world)]
+        placed = []
+        for c in top:
+            load, r = heapq.heappop(loads)
+            placed.append(r)
+            heapq.heappush(loads, (load + c, r))
+        dealt[:head] = torch.tensor(placed, dtype=torch.uint8).to(costs.device)
+    out = torch.empty(n, dtype=torch.uint8, device=costs.device)
+    out[order] = dealt
+    return out
+
+
+def install_owner_deal(graph, world: int, rank: int) -> Tuple[int, int]:
+    """Deal the owners of `graph` over `world` ranks (identical on every rank: the costs and the stable sort are
+    deterministic) and install this rank's share; returns the node range to pass to the `*_owned*` calls (all nodes)."""
+    if world > 1:
+        if world > 256:
+            raise ValueError("owner deal supports at most 256 ranks")
+        graph.set_owner_deal(owner_deal(graph.owner_costs(), world), rank)
+    return 0, graph.num_nodes
+
+
 def owner_sharded_scores(graph, metric: str, group, node_range: Tuple[int, int], node_weights=None,
                          scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Jaccard / Adamic-Adar on `world` GPUs without duplicated work: this rank evaluates the undirected pairs owned by

@@ -142,6 +142,13 @@ int gsp_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t no
 int gsp_jaccard_adamic_adar_owned(const gsp_graph* g, const double* d_node_w, int64_t node_begin, int64_t node_end,
                                   double* d_jaccard_full, double* d_adamic_adar_full, void* stream);
 int gsp_owner_costs(const gsp_graph* g, double* d_cost, void* stream);
+/* Dealt ownership — a finer unit of owner sharding than contiguous node ranges: d_owner_rank is uint8[num_nodes]
+ * (copied into the graph), and from now on every *_owned / *_owned_scatter call on this handle evaluates only the
+ * pairs whose owner o has node_begin <= o < node_end AND d_owner_rank[o] == rank. Dealing the owners in cost order
+ * (gsp_owner_costs, snake order over the ranks) gives every rank the same mix of hub, medium and small owners, so
+ * errors of the cost estimate cancel instead of piling up on the rank that holds the largest hubs. NULL clears the
+ * deal. The plain scoring calls (gsp_jaccard, ...) ignore it. */
+int gsp_graph_set_owner_deal(gsp_graph* g, const uint8_t* d_owner_rank, int32_t rank, void* stream);
 /* Fused scoring + exchange: like the *_owned calls, but every score is stored by the scoring kernel directly into the
  * slice of the rank that owns its position — d_slices is a DEVICE array of `world` pointers, d_slices[k] = base of rank
  * k's fp64[slice_len] slice (position p lives at d_slices[p / slice_len][p % slice_len]); the pointers are typically

@@ -2,7 +2,7 @@
 # usage (inside gpurun --gpus N): bash profiles/tools/r02_multi_gpu_call.sh N [pytest]
 N=$1
 if [ "$2" == "pytest" ]; then
-  timeout 1200 python -m pytest tests/test_gpu_multirank.py tests/test_gpu_parity.py -m gpu -x -q -k "world2 or sharded or select or emulated" 2>&1 | tail -5
+  timeout 1200 python -m pytest tests/test_gpu_multirank.py tests/test_gpu_parity.py -m gpu -x -q -k "world2 or sharded or select or emulated or owner" 2>&1 | tail -5
 fi
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N \
   > gpurun_out/r02_bench_s24_n$N.json 2> gpurun_out/r02_bench_s24_n$N.err

@@ -647,6 +647,37 @@ def test_owner_sharded_scoring_sums_to_the_full_result():
     assert torch.equal(acc_j, full_j) and torch.equal(acc_c, full_counts) and torch.equal(acc_a, full_a)
     length, slices = sharding.equal_slices(g.nnz, 3)
     assert slices[0][0] == 0 and slices[-1][1] == g.nnz and length * 3 >= g.nnz
+    # dealt ownership (gsp_graph_set_owner_deal): owners sorted by cost and dealt in snake order; same contract, and the
+    # plain scoring calls of the same handle are not affected by an installed deal
+    deal = sharding.owner_deal(costs, 3)
+    assert deal.dtype == torch.uint8 and deal.numel() == n and int(deal.max()) == 2
+    loads = [float(costs[deal == r].sum()) for r in range(3)]
+    assert max(loads) - min(loads) <= float(costs.max()), loads       # LPT head + snake tail: apart by at most one owner
+    assert sharding.owner_deal(costs, 3).equal(deal)                   # deterministic (every rank computes its own copy)
+    acc_j.zero_(); acc_a.zero_(); written.zero_()
+    fused_j, fused_a = torch.zeros_like(acc_j), torch.zeros_like(acc_j)
+    for r in range(3):
+        g.set_owner_deal(deal, r)
+        buf = torch.full((g.nnz,), -1.0, dtype=torch.float64, device=DEV)
+        g.jaccard_owned(0, n, buf)
+        touched = buf >= 0
+        written += touched.int()
+        acc_j += torch.where(touched, buf, torch.zeros_like(buf))
+        buf_a = torch.zeros(g.nnz, dtype=torch.float64, device=DEV)
+        g.adamic_adar_owned(w, 0, n, buf_a)
+        acc_a += buf_a
+        bj, ba = torch.zeros_like(acc_j), torch.zeros_like(acc_j)
+        g.jaccard_adamic_adar_owned(w, 0, n, bj, ba)
+        fused_j += bj
+        fused_a += ba
+        assert torch.equal(g.jaccard(), full_j)
+    assert bool((written == 1).all())
+    assert torch.equal(acc_j, full_j) and torch.equal(acc_a, full_a)
+    assert torch.equal(fused_j, full_j) and torch.equal(fused_a, full_a)
+    g.set_owner_deal(None)
+    buf = torch.zeros(g.nnz, dtype=torch.float64, device=DEV)
+    g.jaccard_owned(0, n, buf)
+    assert torch.equal(buf, full_j)
 
 
 @pytest.mark.parametrize("k", [1, 3, 8, 12, 16, 31, 32, 33, 64, 70, 128])
