@@ -37,6 +37,7 @@ constexpr int kATableSlots = 128;          // per-warp hash slots (load factor <
 constexpr int kAThreads = 256;
 constexpr int kAWarps = kAThreads / kWarp;
 constexpr int kARowsPerClaim = 16;
+constexpr int kADealtRowsPerClaim = 32;   // dealt ownership: a claim is screened with one row per lane
 
 __device__ __forceinline__ uint32_t hash_id(int32_t x) { return (uint32_t)x * 0x9E3779B1u; }
 
@@ -152,7 +153,68 @@ struct RangeInfo {
     double* const* slices;
     int64_t slice_len;
     double* const* slices2;   // Jaccard slices of the fused Jaccard + Adamic-Adar pass (kMode 2)
+    double inv_slice_len;     // 1 / slice_len: the slice of a position without a 64-bit division
+    const struct ScatterInfo* scatter;   // the same four values in device memory, for the out-of-line store routine
 };
+struct ScatterInfo {
+    double* const* slices;
+    double* const* slices2;
+    int64_t slice_len;
+    double inv_slice_len;
+};
+
+// p / slice_len for 0 <= p < 2^53: the fp64 estimate is off by at most one
+__device__ __forceinline__ int64_t slice_of(int64_t slice_len, double inv_slice_len, int64_t p) {
+    int64_t k = __double2ll_rd((double)p * inv_slice_len);
+    if (k * slice_len > p) --k;
+    else if ((k + 1) * slice_len <= p) ++k;
+    return k;
+}
+
+// The peer stores of one pair (position p lives at slices[p / slice_len][p % slice_len]).
+__device__ __forceinline__ void scatter_pair(const ScatterInfo* __restrict__ info, int64_t p1, int64_t p2, double score, double jac) {
+    double* const* slices = info->slices;
+    double* const* slices2 = info->slices2;
+    const int64_t slice_len = info->slice_len;
+    const double inv = info->inv_slice_len;
+    const int64_t k1 = slice_of(slice_len, inv, p1);
+    slices[k1][p1 - k1 * slice_len] = score;
+    if (slices2) slices2[k1][p1 - k1 * slice_len] = jac;
+    if (p2 != p1) {
+        const int64_t k2 = slice_of(slice_len, inv, p2);
+        slices[k2][p2 - k2 * slice_len] = score;
+        if (slices2) slices2[k2][p2 - k2 * slice_len] = jac;
+    }
+}
+
+// The whole per-row epilogue of a work item in peer-scatter mode, out of line (its own register allocation): the state
+// arrays follow each other in shared memory (base | acc | len | cursor | cnt | top, `chunk` entries each).
+__device__ __noinline__ void scatter_chunk(const ScatterInfo* __restrict__ info, const int32_t* __restrict__ rev_off,
+                                           const long long* base_s, int chunk, int nb, int64_t p_first, int d_o, int mode) {
+    const double* acc_s = reinterpret_cast<const double*>(base_s + chunk);
+    const int32_t* len_s = reinterpret_cast<const int32_t*>(acc_s + chunk);
+    const int32_t* cnt_s = len_s + 2 * chunk;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const int d_w = len_s[i];
+        if (d_w < 0) continue;  // pair owned by the neighbour
+        const int64_t p1 = p_first + i;
+        const int64_t p2 = base_s[i] + __ldg(rev_off + p1);
+        const int count = cnt_s[i];
+        double jac = 0.0;
+        if (mode != 1) {
+            const double uni = (double)d_o + (double)d_w - (double)count;
+            jac = uni > 0.0 ? __ddiv_rn((double)count, uni) : 0.0;
+        }
+        scatter_pair(info, p1, p2, mode == 0 ? jac : acc_s[i], jac);
+    }
+}
+
+__global__ void fill_scatter_info_kernel(ScatterInfo* info, double* const* slices, double* const* slices2, int64_t slice_len) {
+    info->slices = slices;
+    info->slices2 = slices2;
+    info->slice_len = slice_len;
+    info->inv_slice_len = slice_len > 0 ? 1.0 / (double)slice_len : 0.0;
+}
 
 // Stream row(w)[s, e) through the hash table. kMode 0: returns the number of hits. kMode 1: continues the
 // ordered fp64 accumulation (ids visited in descending order). kMode 2: both (the fused pass: the hit ballots the
@@ -203,14 +265,7 @@ __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64
     }
     const double score = kMode == 0 ? jac : acc;
     if (kScatter) {
-        const int64_t k1 = p1 / r.slice_len;
-        r.slices[k1][p1 - k1 * r.slice_len] = score;
-        if (kMode == 2) r.slices2[k1][p1 - k1 * r.slice_len] = jac;
-        if (p2 != p1) {
-            const int64_t k2 = p2 / r.slice_len;
-            r.slices[k2][p2 - k2 * r.slice_len] = score;
-            if (kMode == 2) r.slices2[k2][p2 - k2 * r.slice_len] = jac;
-        }
+        scatter_pair(r.scatter, p1, p2, score, jac);
         return;
     }
     if (p1 >= r.e_begin && p1 < r.e_end) {
@@ -226,7 +281,11 @@ __device__ __forceinline__ void write_pair(const RangeInfo& r, int64_t p1, int64
 }
 
 // ---- level A: one warp per low-degree owner --------------------------------------------------------------
-template <int kMode, bool kScatter>
+// kDealt (dealt ownership: most rows of a claim belong to other ranks): a claim of 32 rows is screened with one row per lane,
+// so a foreign row costs a share of one ballot instead of a dependent indptr round trip of the whole warp (one of eight
+// ranks: 1.13 -> 0.73 ms). Without a deal the rows are visited one after the other: screening every claim was a net loss
+// there (4.26 -> 4.56 ms), and so was sharing one loop between the two modes (5.0 ms).
+template <int kMode, bool kScatter, bool kDealt>
 __global__ void __launch_bounds__(kAThreads)
 warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                   const int32_t* __restrict__ rev_off, RangeInfo r,
@@ -237,50 +296,71 @@ warp_owner_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* 
     int32_t* slots = tables[threadIdx.x >> 5];
     constexpr uint32_t mask = kATableSlots - 1;
     constexpr int shift = 32 - 7;
+    // one owner row: hash its (<= 64) neighbours into the warp's table, stream the rows of the neighbours it owns
+    auto score_owner = [&](int32_t o, int64_t a0, int d_o) {
+        const int64_t a1 = a0 + d_o;
+        const bool row_in_range = r.full || (a0 < r.e_end && a1 > r.e_begin);
+        // neighbours in registers: lane holds elements lane and lane + 32
+        const int32_t nb0 = lane < d_o ? __ldg(indices + a0 + lane) : INT_MAX;
+        const int32_t nb1 = lane + 32 < d_o ? __ldg(indices + a0 + lane + 32) : INT_MAX;
+        if (!row_in_range) {  // only neighbours whose own row meets the range matter: any of them?
+            const bool any0 = lane < d_o && nb0 >= r.row_lo && nb0 <= r.row_hi;
+            const bool any1 = lane + 32 < d_o && nb1 >= r.row_lo && nb1 <= r.row_hi;
+            if (!__any_sync(0xffffffffu, any0 || any1)) return;
+        }
+        __syncwarp();
+        for (int i = lane; i < kATableSlots; i += kWarp) slots[i] = -1;
+        __syncwarp();
+        if (lane < d_o) hash_insert(slots, mask, shift, nb0);
+        if (lane + 32 < d_o) hash_insert(slots, mask, shift, nb1);
+        __syncwarp();
+        for (int j = 0; j < d_o; ++j) {
+            const int32_t w = __shfl_sync(0xffffffffu, j < 32 ? nb0 : nb1, j & 31);
+            const int64_t b0 = __ldg(indptr + w);
+            const int d_w = (int)(__ldg(indptr + w + 1) - b0);
+            if (other_owns(d_w, w, d_o, o)) continue;
+            const int64_t p1 = a0 + j;
+            if (!r.full) {
+                const bool p1_in = p1 >= r.e_begin && p1 < r.e_end;
+                const bool w_in = b0 < r.e_end && b0 + d_w > r.e_begin;
+                if (!p1_in && !w_in) continue;
+            }
+            int count = 0;
+            double acc = 0.0;
+            stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc);
+            if (lane == 0)
+                write_pair<kMode, kScatter>(r, p1, b0 + __ldg(rev_off + p1), d_o, d_w, count, acc, inter_out, score_out, jaccard_out);
+        }
+    };
+    constexpr int kRows = kDealt ? kADealtRowsPerClaim : kARowsPerClaim;
     for (;;) {
         unsigned long long first = 0;
-        if (lane == 0) first = atomicAdd(counter, (unsigned long long)kARowsPerClaim);
+        if (lane == 0) first = atomicAdd(counter, (unsigned long long)kRows);
         first = __shfl_sync(0xffffffffu, first, 0);
         first += (unsigned long long)r.owner_lo;
         if ((int64_t)first >= r.owner_hi) break;
-        const int64_t last = min((int64_t)first + kARowsPerClaim, (int64_t)r.owner_hi);
-        for (int64_t o64 = (int64_t)first; o64 < last; ++o64) {
-            const int32_t o = (int32_t)o64;
-            const int64_t a0 = __ldg(indptr + o), a1 = __ldg(indptr + o + 1);
-            const int d_o = (int)(a1 - a0);
-            if (d_o == 0 || d_o > kWarpOwnerMax) continue;
-            if (r.deal && r.deal[o] != r.deal_rank) continue;
-            const bool row_in_range = r.full || (a0 < r.e_end && a1 > r.e_begin);
-            // neighbours in registers: lane holds elements lane and lane + 32
-            const int32_t nb0 = lane < d_o ? __ldg(indices + a0 + lane) : INT_MAX;
-            const int32_t nb1 = lane + 32 < d_o ? __ldg(indices + a0 + lane + 32) : INT_MAX;
-            if (!row_in_range) {  // only neighbours whose own row meets the range matter: any of them?
-                const bool any0 = lane < d_o && nb0 >= r.row_lo && nb0 <= r.row_hi;
-                const bool any1 = lane + 32 < d_o && nb1 >= r.row_lo && nb1 <= r.row_hi;
-                if (!__any_sync(0xffffffffu, any0 || any1)) continue;
+        const int64_t last = min((int64_t)first + kRows, (int64_t)r.owner_hi);
+        if constexpr (kDealt) {
+            const int64_t cand = (int64_t)first + lane;
+            int64_t cand_a0 = 0;
+            int cand_d = 0;
+            if (cand < last && r.deal[cand] == r.deal_rank) {
+                cand_a0 = __ldg(indptr + cand);
+                cand_d = (int)(__ldg(indptr + cand + 1) - cand_a0);
+                if (cand_d > kWarpOwnerMax) cand_d = 0;
             }
-            __syncwarp();
-            for (int i = lane; i < kATableSlots; i += kWarp) slots[i] = -1;
-            __syncwarp();
-            if (lane < d_o) hash_insert(slots, mask, shift, nb0);
-            if (lane + 32 < d_o) hash_insert(slots, mask, shift, nb1);
-            __syncwarp();
-            for (int j = 0; j < d_o; ++j) {
-                const int32_t w = __shfl_sync(0xffffffffu, j < 32 ? nb0 : nb1, j & 31);
-                const int64_t b0 = __ldg(indptr + w);
-                const int d_w = (int)(__ldg(indptr + w + 1) - b0);
-                if (other_owns(d_w, w, d_o, o)) continue;
-                const int64_t p1 = a0 + j;
-                if (!r.full) {
-                    const bool p1_in = p1 >= r.e_begin && p1 < r.e_end;
-                    const bool w_in = b0 < r.e_end && b0 + d_w > r.e_begin;
-                    if (!p1_in && !w_in) continue;
-                }
-                int count = 0;
-                double acc = 0.0;
-                stream_row<kMode>(indices + b0, 0, d_w, slots, mask, shift, o, node_w, count, acc);
-                if (lane == 0)
-                    write_pair<kMode, kScatter>(r, p1, b0 + __ldg(rev_off + p1), d_o, d_w, count, acc, inter_out, score_out, jaccard_out);
+            unsigned todo = __ballot_sync(0xffffffffu, cand_d > 0);
+            while (todo) {
+                const int pick = __ffs(todo) - 1;
+                todo &= todo - 1;
+                score_owner((int32_t)first + pick, __shfl_sync(0xffffffffu, cand_a0, pick), __shfl_sync(0xffffffffu, cand_d, pick));
+            }
+        } else {
+            for (int64_t o64 = (int64_t)first; o64 < last; ++o64) {
+                const int64_t a0 = __ldg(indptr + o64);
+                const int d_o = (int)(__ldg(indptr + o64 + 1) - a0);
+                if (d_o == 0 || d_o > kWarpOwnerMax) continue;
+                score_owner((int32_t)o64, a0, d_o);
             }
         }
     }
@@ -582,11 +662,15 @@ __device__ __forceinline__ void cta_owner_body(const OwnerItem* __restrict__ ite
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < nb; i += nthreads) {
-            if (len_s[i] < 0) continue;  // pair owned by the neighbour, or outside the range
-            const int64_t p1 = a0 + j0 + i;
-            write_pair<kMode, kScatter>(r, p1, base_s[i] + __ldg(rev_off + p1), d_o, len_s[i], cnt_s[i], acc_s[i], inter_out, score_out,
-                                        jaccard_out);
+        if constexpr (kScatter) {
+            scatter_chunk(r.scatter, rev_off, base_s, cls.chunk, nb, a0 + j0, d_o, kMode);
+        } else {
+            for (int i = threadIdx.x; i < nb; i += nthreads) {
+                if (len_s[i] < 0) continue;  // pair owned by the neighbour, or outside the range
+                const int64_t p1 = a0 + j0 + i;
+                write_pair<kMode, kScatter>(r, p1, base_s[i] + __ldg(rev_off + p1), d_o, len_s[i], cnt_s[i], acc_s[i], inter_out,
+                                            score_out, jaccard_out);
+            }
         }
     }
 }
@@ -599,13 +683,11 @@ __device__ __forceinline__ void cta_owner_body(const OwnerItem* __restrict__ ite
 #define GSP_OWNER_ARGS items, num_items, cls, indptr, indices, rev_off, r, node_w, inter_out, score_out, jaccard_out, counter
 
 // No launch bounds: the natural allocation is 32-40 registers (two 768-thread hub CTAs per SM); bounding every
-// instantiation measured 5 % slower. Only the fused pass with peer scatter needs the cap (47 registers otherwise).
+// instantiation measured 5 % slower. The peer-scatter instantiations reach 40 only with their per-row epilogue out of
+// line (`scatter_chunk`); inlined, the fused one took 44-47 and needed a cap that cost ~6 % of every launch.
 template <int kMode, bool kScatter>
 __global__ void cta_owner_kernel(GSP_OWNER_PARAMS) {
     cta_owner_body<kMode, kScatter>(GSP_OWNER_ARGS);
-}
-__global__ void __launch_bounds__(768, 2) cta_owner_kernel_both_scatter(GSP_OWNER_PARAMS) {
-    cta_owner_body<2, true>(GSP_OWNER_ARGS);
 }
 
 // ---- work items for level B (built once per graph) -----------------------------------------------------------
@@ -793,7 +875,6 @@ int launch_class(const OwnerClass& cls, const OwnerItem* items, int64_t count, i
     if (count <= 0) return GSP_OK;
     const size_t smem = owner_smem_bytes(cls, kMode != 0);
     auto kernel = cta_owner_kernel<kMode, kScatter>;
-    if constexpr (kMode == 2 && kScatter) kernel = cta_owner_kernel_both_scatter;
     GSP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int64_t blocks = (int64_t)kNumSMs * ctas_per_sm;
     if (blocks > count) blocks = count;
@@ -810,7 +891,14 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
     if (g->n == 0 || e_end == e_begin || owner_hi <= owner_lo) return GSP_OK;
     if (int rc = ensure_items(g, s)) return rc;
     RangeInfo r{e_begin, e_end, 0, 0, e_begin == 0 && e_end == g->nnz, (int32_t)owner_lo, (int32_t)owner_hi,
-                dealt ? g->deal : nullptr, g->deal_rank, slices, slice_len, slices2};
+                dealt ? g->deal : nullptr, g->deal_rank, slices, slice_len, slices2, slice_len > 0 ? 1.0 / (double)slice_len : 0.0, nullptr};
+    Scratch<ScatterInfo> scatter_info;
+    if (kScatter) {
+        GSP_CUDA_TRY(scatter_info.alloc(1, s));
+        fill_scatter_info_kernel<<<1, 1, 0, s>>>(scatter_info.ptr, slices, kMode == 2 ? slices2 : nullptr, slice_len);
+        GSP_CHECK_LAUNCH();
+        r.scatter = scatter_info.ptr;
+    }
     if (!r.full) {
         Scratch<int32_t> rr;
         GSP_CUDA_TRY(rr.alloc(2, s));
@@ -847,9 +935,15 @@ int launch(Graph* g, int64_t e_begin, int64_t e_end, int64_t owner_lo, int64_t o
                                      jaccard, counters.ptr, s)) return rc;
     if (int rc = launch_class<kMode, kScatter>(kMediumClass, items, num_medium, 7, g, r, node_w, inter, score, jaccard,
                                      counters.ptr + 1, s)) return rc;
-    const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
-    warp_owner_kernel<kMode, kScatter><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter,
-                                                                            score, jaccard, counters.ptr + 2);
+    if (r.deal) {
+        const int64_t claims = (owner_hi - owner_lo + kADealtRowsPerClaim - 1) / kADealtRowsPerClaim;
+        warp_owner_kernel<kMode, kScatter, true><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(
+            g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter, score, jaccard, counters.ptr + 2);
+    } else {
+        const int64_t claims = (owner_hi - owner_lo + kARowsPerClaim - 1) / kARowsPerClaim;
+        warp_owner_kernel<kMode, kScatter, false><<<grid_for(claims, kAWarps, 8), kAThreads, 0, s>>>(
+            g->n, g->indptr, g->indices, g->rev_off, r, node_w, inter, score, jaccard, counters.ptr + 2);
+    }
     GSP_CHECK_LAUNCH();
     return GSP_OK;
 }

@@ -128,6 +128,25 @@ def test_partition_helpers():
     assert sum(hi - lo for lo, hi in slices) == 10 and all(a[1] == b[0] for a, b in zip(slices, slices[1:]))
 
 
+def test_owner_deal_balances_an_outlier_and_is_deterministic():
+    """`sharding.owner_deal`: the heaviest owners placed greedily on the least-loaded rank, the rest dealt in snake order."""
+    g = torch.Generator().manual_seed(4)
+    costs = torch.rand(50000, generator=g, dtype=torch.float64) ** 6 * 1e6
+    costs[17] = 3.0 * float(costs.max())                  # one owner with three times the work of the runner-up
+    costs[100:200] = 0.0                                   # owners with nothing to do
+    for world in (2, 3, 8):
+        deal = sharding.owner_deal(costs, world)
+        assert deal.dtype == torch.uint8 and deal.numel() == costs.numel() and int(deal.max()) == world - 1
+        assert sharding.owner_deal(costs.clone(), world).equal(deal)
+        loads = torch.stack([costs[deal == r].sum() for r in range(world)])
+        assert float(loads.max() - loads.min()) <= 1e-3 * float(loads.mean()), (world, loads.tolist())
+        counts = torch.bincount(deal.long(), minlength=world)
+        assert int(counts.max() - counts.min()) <= 0.02 * costs.numel()       # and a similar number of owners each
+    few = sharding.owner_deal(torch.tensor([5.0, 1.0, 1.0]), 2)               # fewer owners than one snake cycle
+    assert few.tolist() == [0, 1, 1]
+    assert sharding.owner_deal(torch.zeros(0, dtype=torch.float64), 4).numel() == 0
+
+
 class _OwnedScoresStandIn:
     """Stand-in for engine.DeviceGraph in the owner-sharded exchange: position p is "owned" by node p % num_nodes, its
     Jaccard score is p + 1 and its Adamic-Adar score 1000 + p (the CUDA calls write exactly the owned positions of
