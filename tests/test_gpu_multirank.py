@@ -2,8 +2,9 @@
 
 Every rank builds `GraphSparsifier(data, device, group=...)` — the sharded engine behind the reference API — and checks
 its slices / masks / kept edge lists against (1) the single-GPU engine on the same device, bit for bit, and (2) the C
-oracle. Covers the peer-store fused Jaccard + Adamic-Adar pass, the row-sharded feature normalisation, the distributed
-radix select, the sharded "-W" weights (min / max all-reduce), and the replicated degree-aware / sampled variants
+oracle. Covers the peer-store fused Jaccard + Adamic-Adar pass over dealt owners, the distributed radix select with its
+fused per-rank tail (mask slice, kept columns, "-W" weights from the boundary and best keys), and the replicated
+degree-aware / sampled variants
 (reference src/sparsification/core.py:193-461, scripts/nb05_roman_empire/roman_empire_gpu.py:248-256)."""
 import os
 import socket
