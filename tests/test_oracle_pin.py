@@ -224,9 +224,9 @@ def test_geodesic_port_matches_goldens():
 
 
 def test_pyg_port_matches_dense_normalised_adjacency():
-    """oracle/pyg_port.py (restatement of torch_geometric's gcn_norm + propagate; the library itself is not installed, so this
-    is the only pin it has) against a dense D^-1/2 (A + I') D^-1/2 built independently, with self loops that keep their
-    weight, duplicate edges and isolated nodes."""
+    """oracle/pyg_port.py (restatement of torch_geometric's gcn_norm + propagate; the library itself is not installed, so it
+    stays "parity unpinned" against PyG) against a dense D^-1/2 (A + I') D^-1/2 built independently, with self loops that keep
+    their weight, duplicate edges and isolated nodes — and against NetworkX's normalised Laplacian on the karate club."""
     from oracle import pyg_port
 
     rng = np.random.default_rng(0)
@@ -257,3 +257,22 @@ def test_pyg_port_matches_dense_normalised_adjacency():
     ring = np.hstack([ring, ring[::-1]])
     _, rw = pyg_port.gcn_norm(ring, None, 8)
     assert np.allclose(rw, 1.0 / 3.0, rtol=2e-7)
+    # a second, library-made pin: NetworkX's normalised Laplacian of the graph with unit self loops added is
+    # I - D^-1/2 (A + I) D^-1/2 (row sums of the adjacency matrix, so a loop counts once — the GCN convention)
+    import networkx as nx
+
+    kc = nx.karate_club_graph()
+    m = kc.number_of_nodes()
+    for weight in (None, "weight"):
+        g = nx.Graph()
+        g.add_nodes_from(range(m))
+        g.add_weighted_edges_from((u, v, float(d["weight"]) if weight else 1.0) for u, v, d in kc.edges(data=True))
+        pairs = np.array([(u, v) for u, v in g.edges()] + [(v, u) for u, v in g.edges()]).T
+        vals = np.array([g[u][v]["weight"] for u, v in pairs.T], dtype=np.float32)
+        g.add_weighted_edges_from((i, i, 1.0) for i in range(m))
+        want = np.eye(m) - nx.normalized_laplacian_matrix(g, nodelist=range(m), weight="weight").toarray()
+        k_ei, k_w = pyg_port.gcn_norm(pairs, vals if weight else None, m)
+        got = np.zeros((m, m))
+        for (r, c), v in zip(k_ei.T, k_w):
+            got[c, r] += v
+        assert np.abs(got - want).max() < 5e-7, weight
