@@ -22,9 +22,11 @@ separate calls; GSP_BENCH_FUSED=0 times two passes); selection + mask + compacti
            the ncu DRAM traffic, every per-method line, the other BASELINE configs (1-4) and the per-rank spread beside it.
 
 N > 1 (device-timed): FeatCos scores a contiguous edge slice per rank; Jaccard / Adamic-Adar are owner-sharded (each
-undirected pair on exactly one rank) with every score stored by the scoring kernel straight into the slice of the rank
-that owns its position (NVLink symmetric memory; NCCL reduce-scatter as the fallback); selection all-reduces 16 KB radix
-histograms. Fixed graph => "scaling": "strong".
+undirected pair on exactly one rank; owners dealt to the ranks in cost order, GSP_BENCH_PARTITION=ranges: contiguous node
+ranges) with every score stored by the scoring kernel straight into the slice of the rank that owns its position (NVLink
+symmetric memory; NCCL reduce-scatter as the fallback); selection all-gathers 16 KB radix slots and two counters per rank,
+mask + compaction are one emit per rank (`engine.ShardedSelect`). Fixed graph => "scaling": "strong".
+Clocks and throttle reasons are sampled during the timed region through NVML (GSP_BENCH_CLOCKS=smi: the nvidia-smi CLI).
 """
 from __future__ import annotations
 
